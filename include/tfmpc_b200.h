@@ -1,0 +1,214 @@
+/*
+ * tfmpc_b200 -- C ABI of the B200-native batched LQR / iLQR solver.
+ *
+ * This is the drop-in boundary for the hot path of thiagopbueno/tf-mpc v0.7.0.  The
+ * reference has no FFI of its own (it is pure Python on TensorFlow), so each entry point
+ * cites the reference *Python* interface it replaces (paths relative to the reference
+ * repo root).  The Python mirror in tfmpc_b200/ (same class / method names as the
+ * reference) reaches these symbols through ctypes (tfmpc_b200/_native.py); tensors are
+ * handed over zero-copy: the shim exports each torch tensor as a DLPack capsule, asks
+ * tfmpc_dl_unpack() to validate it and to return the raw pointer, and passes plain
+ * pointers + sizes to the compute entry points below.
+ *
+ * Two builds of the same sources:  libtfmpc_b200.so      tfmpc_real = float   (product)
+ *                                  libtfmpc_b200_f64.so  tfmpc_real = double  (verification build)
+ *
+ * Conventions
+ *  - every function returns 0 on success, a negative TFMPC_E_* code on failure; the text
+ *    of the last failure on the calling thread is tfmpc_last_error().  No exception or
+ *    abort ever crosses this boundary.
+ *  - all tensor arguments are DEVICE pointers to dense row-major arrays in the reference's
+ *    layouts, unless the function name ends in _host.  Nothing is retained after return.
+ *  - all work is enqueued on the caller's stream (a cudaStream_t passed as void*; NULL =
+ *    legacy default stream); no hidden synchronisation, no global mutable state, so calls
+ *    are re-entrant across streams and threads.  The *_host variants are the exception:
+ *    they copy host->device, solve, copy device->host and synchronise their stream.
+ *  - per-problem numerical trouble (non-PD Q_uu, NaN, iteration cap) is reported in the
+ *    per-problem status / stats arrays, never as a call failure.
+ *  - there is no CPU fallback: without a CUDA device every compute entry point fails with
+ *    TFMPC_E_CUDA.
+ */
+#ifndef TFMPC_B200_H
+#define TFMPC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifdef TFMPC_F64
+typedef double tfmpc_real;
+#else
+typedef float tfmpc_real;
+#endif
+
+#define TFMPC_ABI_VERSION 1
+#define TFMPC_MAX_DIM 32   /* max state / action dimension of an environment */
+#define TFMPC_MAX_ZONES 8  /* max deceleration zones of the Navigation environment */
+
+enum {
+  TFMPC_OK = 0,
+  TFMPC_E_INVALID = -1,     /* bad argument (null pointer, size out of range, ...) */
+  TFMPC_E_UNSUPPORTED = -2, /* valid request this build has no kernel for */
+  TFMPC_E_CUDA = -3,        /* CUDA runtime error, text in tfmpc_last_error() */
+  TFMPC_E_DLPACK = -4,      /* DLPack tensor failed validation */
+  TFMPC_E_WORKSPACE = -5    /* workspace too small */
+};
+
+/* environment kinds (reference classes) */
+enum {
+  TFMPC_ENV_NAVLQR = 0,     /* tfmpc/envs/lqr/navigation/__init__.py:8  NavigationLQR */
+  TFMPC_ENV_NAVIGATION = 1, /* tfmpc/envs/navigation/__init__.py:9      Navigation    */
+  TFMPC_ENV_RESERVOIR = 2,  /* tfmpc/envs/reservoir/__init__.py:9       Reservoir     */
+  TFMPC_ENV_HVAC = 3        /* tfmpc/envs/hvac/__init__.py:8            HVAC          */
+};
+
+/* per-problem status written by the solvers */
+enum {
+  TFMPC_ST_CONVERGED = 0,   /* g_norm < atol or residual < atol (ilqr.py:245-257) */
+  TFMPC_ST_MAXITER = 1,     /* max_iterations exhausted (ilqr.py:227) */
+  TFMPC_ST_NONPD = 2,       /* a box-QP / inverse factorisation failed (optimization.py:47-51; the reference aborts) */
+  TFMPC_ST_REGLOOP = 3,     /* regularisation loop guard tripped (the reference would spin, ilqr.py:238) */
+  TFMPC_ST_NAN = 4          /* NaN in the gradient norm */
+};
+
+typedef struct tfmpc_env tfmpc_env_t; /* opaque */
+
+/* iLQR hyper-parameters: the reference's constructor kwargs and defaults, ilqr.py:27-37 */
+typedef struct {
+  double atol;          /* 5e-3 */
+  int32_t max_iterations; /* 100 */
+  double mu_min;        /* 1e-6 */
+  double delta_0;       /* 2.0 */
+  double c1;            /* 0.0 */
+  double alpha_min;     /* 1e-3 */
+} tfmpc_ilqr_opts_t;
+
+/* ---------------------------------------------------------------- library */
+int tfmpc_abi_version(void);
+/* sizeof(tfmpc_real) of this build: 4 or 8 */
+int tfmpc_real_bytes(void);
+const char *tfmpc_last_error(void);
+void tfmpc_ilqr_default_opts(tfmpc_ilqr_opts_t *opts);
+
+/* Validate a borrowed DLManagedTensor* (DLPack ABI v0.x, as produced by
+ * torch.utils.dlpack.to_dlpack) and return its data pointer.  The deleter is NEVER called.
+ *   want_device: 2 = must be CUDA, 1 = must be CPU, 0 = either
+ *   want_code:   0 = tfmpc_real of this build, 1 = int32
+ * shape must have room for 8 entries.  Fails unless the tensor is compact row-major. */
+int tfmpc_dl_unpack(const void *dl_managed_tensor, int want_device, int want_code, void **data, int32_t *ndim,
+                    int64_t *shape, int32_t *device_id);
+
+/* ---------------------------------------------------------------- LQR
+ * Replaces LQR.solve = LQR.backward + LQR.forward (tfmpc/solvers/lqr.py:59-166) for B
+ * independent problems.  F [n,n+m], f [n], C [n+m,n+m], c [n+m] per problem; a batch stride
+ * (sF, sf, sC, sc, in elements) of 0 shares that array across the batch (config C2 shares F, f,
+ * C and varies c).  Outputs: states [B,T+1,n], actions [B,T,m], costs [B,T+1]; optional (nullable)
+ * K [B,T,m,n], k [B,T,m], V [B,T,n,n], v [B,T,n], cst [B,T] = the policy / value_fn lists of
+ * lqr.py:126-129.  status [B] (nullable): 0 or TFMPC_ST_NONPD when Q_uu was singular.
+ * terminal_zero != 0 selects V_T = v_T = 0 without a final cost (the README.md:74-92 table);
+ * 0 is the v0.7.0 source (lqr.py:67-68,154-155). */
+int tfmpc_lqr_solve(int64_t B, int n, int m, int T, const tfmpc_real *F, int64_t sF, const tfmpc_real *f, int64_t sf,
+                    const tfmpc_real *C, int64_t sC, const tfmpc_real *c, int64_t sc, const tfmpc_real *x0,
+                    int terminal_zero, tfmpc_real *states, tfmpc_real *actions, tfmpc_real *costs, tfmpc_real *K,
+                    tfmpc_real *k, tfmpc_real *V, tfmpc_real *v, tfmpc_real *cst, int32_t *status, void *stream);
+
+/* LQR.forward(policy, x0, T) (lqr.py:131-161) for a caller-supplied policy K [B,T,m,n], k [B,T,m]. */
+int tfmpc_lqr_forward(int64_t B, int n, int m, int T, const tfmpc_real *F, int64_t sF, const tfmpc_real *f, int64_t sf,
+                      const tfmpc_real *C, int64_t sC, const tfmpc_real *c, int64_t sc, const tfmpc_real *K,
+                      const tfmpc_real *k, const tfmpc_real *x0, tfmpc_real *states, tfmpc_real *actions,
+                      tfmpc_real *costs, void *stream);
+/* LQR.transition / LQR.cost / LQR.final_cost (lqr.py:36-57) for R rows: x [R,n], u [R,m] (may be NULL
+ * when only final_cost is wanted) -> x_next [R,n], cost [R], final_cost [R]; any output may be NULL. */
+int tfmpc_lqr_step(int64_t R, int n, int m, const tfmpc_real *F, int64_t sF, const tfmpc_real *f, int64_t sf,
+                   const tfmpc_real *C, int64_t sC, const tfmpc_real *c, int64_t sc, const tfmpc_real *x,
+                   const tfmpc_real *u, tfmpc_real *x_next, tfmpc_real *cost, tfmpc_real *final_cost, void *stream);
+
+/* ---------------------------------------------------------------- environments
+ * Replaces Env.load(config) of the four env classes (e.g. navigation/__init__.py:86-96).
+ * `params` is a HOST array of doubles, copied; layout per kind:
+ *   NAVLQR      goal[n] beta low[n] high[n]                       (+-inf = unbounded)
+ *   NAVIGATION  goal[2] low[2] high[2] center[nz][2] decay[nz]
+ *   RESERVOIR   max_res_cap lower_bound upper_bound low_penalty high_penalty set_point_penalty
+ *               rain_shape rain_scale (each [n]) downstream[n][n]
+ *   HVAC        temp_outside temp_hall temp_lower_bound temp_upper_bound R_outside R_hall capacity
+ *               air_max adj_outside adj_hall (each [n]) R_wall[n][n] adj[n][n]
+ */
+int tfmpc_env_create(int kind, int n, int m, int nz, const double *params, int64_t nparams, tfmpc_env_t **env);
+int tfmpc_env_destroy(tfmpc_env_t *env);
+/* state_size, action_size, action_space.is_bounded(), and low/high (host copies, length m) */
+int tfmpc_env_info(const tfmpc_env_t *env, int32_t *n, int32_t *m, int32_t *bounded, double *low, double *high);
+
+/* transition(state, action, batch=True) and cost(state, action, batch=True) for R rows:
+ * x [R,n], u [R,m] -> x_next [R,n] (nullable), cost [R] (nullable).
+ * (navigation/__init__.py:34-54 etc.; deterministic cec=True dynamics) */
+int tfmpc_env_step(const tfmpc_env_t *env, int64_t R, const tfmpc_real *x, const tfmpc_real *u, tfmpc_real *x_next,
+                   tfmpc_real *cost, void *stream);
+/* final_cost(state): x [R,n] -> cost [R] */
+int tfmpc_env_final_cost(const tfmpc_env_t *env, int64_t R, const tfmpc_real *x, tfmpc_real *cost, void *stream);
+/* DiffEnv.get_linear_transition + get_quadratic_cost (tfmpc/envs/diffenv.py:13-83) with analytic
+ * derivatives: x [R,n], u [R,m] -> f_x [R,n,n] f_u [R,n,m] l [R] l_x [R,n] l_u [R,m] l_xx [R,n,n]
+ * l_uu [R,m,m] l_ux [R,m,n] l_xu [R,n,m]; any output may be NULL. */
+int tfmpc_env_linearize(const tfmpc_env_t *env, int64_t R, const tfmpc_real *x, const tfmpc_real *u, tfmpc_real *f_x,
+                        tfmpc_real *f_u, tfmpc_real *l, tfmpc_real *l_x, tfmpc_real *l_u, tfmpc_real *l_xx,
+                        tfmpc_real *l_uu, tfmpc_real *l_ux, tfmpc_real *l_xu, void *stream);
+/* DiffEnv.get_quadratic_final_cost (diffenv.py:85-101): x [R,n] -> l [R], l_x [R,n], l_xx [R,n,n] */
+int tfmpc_env_final_quad(const tfmpc_env_t *env, int64_t R, const tfmpc_real *x, tfmpc_real *l, tfmpc_real *l_x,
+                         tfmpc_real *l_xx, void *stream);
+
+/* ---------------------------------------------------------------- box-QP
+ * utils/optimization.py:6-101 projected_newton_qp for B independent problems of size m:
+ * H [B,m,m], q/low/high [B,m], x [B,m] in (start) / out (solution); Hfree [B,m,m] receives the
+ * Cholesky factor of H[free,free] in its leading nfree x nfree block; free [B,m] int32 flags;
+ * nfree [B]; status [B]. */
+int tfmpc_boxqp(int64_t B, int m, const tfmpc_real *H, const tfmpc_real *q, const tfmpc_real *low,
+                const tfmpc_real *high, tfmpc_real *x, tfmpc_real *Hfree, int32_t *isfree, int32_t *nfree,
+                int32_t *status, void *stream);
+
+/* ---------------------------------------------------------------- iLQR stages (tests/test_ilqr.py:48-109)
+ * iLQR.start (ilqr.py:53-82) with the initial actions supplied instead of drawn:
+ * x0 [B,n], u_init [B,T,m] -> states [B,T+1,n], actions [B,T,m] (copy of u_init), costs [B,T+1]. */
+int tfmpc_ilqr_start(const tfmpc_env_t *env, int64_t B, int T, const tfmpc_real *x0, const tfmpc_real *u_init,
+                     tfmpc_real *states, tfmpc_real *actions, tfmpc_real *costs, void *stream);
+/* iLQR.derivatives + iLQR.backward fused (ilqr.py:84-172, controllers :357-387): linearises along
+ * (states, actions) and sweeps t = T-1..0.  -> K [B,T,m,n], k [B,T,m], J/dV1/dV2 [B], status [B]
+ * (0 ok, 1 = unconstrained Cholesky failed -- the caller's retry rule is ilqr.py:305-309,
+ * 2 = box-QP factorisation failed). */
+int tfmpc_ilqr_backward(const tfmpc_env_t *env, int64_t B, int T, const tfmpc_real *states, const tfmpc_real *actions,
+                        double mu, tfmpc_real *K, tfmpc_real *k, tfmpc_real *J, tfmpc_real *dV1, tfmpc_real *dV2,
+                        int32_t *status, void *stream);
+/* iLQR.forward (ilqr.py:174-212) -> xs [B,T+1,n], us [B,T,m], cs [B,T+1], J [B], residual [B] */
+int tfmpc_ilqr_forward(const tfmpc_env_t *env, int64_t B, int T, const tfmpc_real *states, const tfmpc_real *actions,
+                       const tfmpc_real *K, const tfmpc_real *k, double alpha, tfmpc_real *xs, tfmpc_real *us,
+                       tfmpc_real *cs, tfmpc_real *J, tfmpc_real *residual, void *stream);
+
+/* ---------------------------------------------------------------- iLQR solve
+ * iLQR.solve (ilqr.py:214-283) for B problems with the whole schedule (mu, delta, convergence,
+ * line search, ilqr.py:236-277,285-355) on the device.  x0 [B,n], u_init [B,T,m] (the reference
+ * draws these at random, ilqr.py:70; pass them explicitly) -> states [B,T+1,n], actions [B,T,m],
+ * costs [B,T+1], stats [B,4] int32 = {iteration index returned by the reference, backward passes,
+ * reference-semantics rollouts, TFMPC_ST_* status}.
+ * workspace: device scratch of at least tfmpc_ilqr_workspace_bytes() bytes, 256-byte aligned. */
+int64_t tfmpc_ilqr_workspace_bytes(const tfmpc_env_t *env, int64_t B, int T);
+int tfmpc_ilqr_solve(const tfmpc_env_t *env, int64_t B, int T, const tfmpc_real *x0, const tfmpc_real *u_init,
+                     const tfmpc_ilqr_opts_t *opts, tfmpc_real *states, tfmpc_real *actions, tfmpc_real *costs,
+                     int32_t *stats, void *workspace, int64_t workspace_bytes, void *stream);
+/* Same call with HOST buffers (pageable or pinned): copies inputs to the device, solves, copies
+ * the results back and synchronises.  Device scratch is cached inside the env handle. */
+int tfmpc_ilqr_solve_host(tfmpc_env_t *env, int64_t B, int T, const tfmpc_real *x0, const tfmpc_real *u_init,
+                          const tfmpc_ilqr_opts_t *opts, tfmpc_real *states, tfmpc_real *actions, tfmpc_real *costs,
+                          int32_t *stats, void *stream);
+int tfmpc_lqr_solve_host(int64_t B, int n, int m, int T, const tfmpc_real *F, int64_t sF, const tfmpc_real *f, int64_t sf,
+                         const tfmpc_real *C, int64_t sC, const tfmpc_real *c, int64_t sc, const tfmpc_real *x0,
+                         int terminal_zero, tfmpc_real *states, tfmpc_real *actions, tfmpc_real *costs, int32_t *status,
+                         void *stream);
+
+/* number of kernels this library has launched on behalf of the calling process (monotonic) */
+int64_t tfmpc_kernel_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TFMPC_B200_H */

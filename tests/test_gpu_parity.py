@@ -1,0 +1,476 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via tfmpc_b200) against the CPU oracle on the
+same seeded inputs, against the committed golden fixtures produced by the reference itself, and --
+at BASELINE.json's full batch sizes -- through size-independent properties.
+
+Tolerances (BASELINE.json north_star): LQR gains/trajectories 1e-5 relative in fp32; converged iLQR
+total cost and actions 1e-4 relative with the same iteration count (a +-1 difference is tolerated on
+a small fraction of problems and that fraction is asserted); the fp64 verification build is held
+to 1e-9.  Reservoir is chaotic (SURVEY finding 7): per-stage parity plus distributional parity.
+"""
+import numpy as np
+import pytest
+import torch
+
+from _util import cfg_of, golden, golden_names, rel, tol
+
+pytestmark = pytest.mark.gpu
+
+PRECS = ["f32", "f64"]
+
+
+def _dt(prec):
+    return torch.float32 if prec == "f32" else torch.float64
+
+
+def _cu(a, prec):
+    return torch.as_tensor(np.ascontiguousarray(a)).to(device="cuda", dtype=_dt(prec)).contiguous()
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+@pytest.fixture(scope="module", params=PRECS)
+def prec(request):
+    return request.param
+
+
+@pytest.fixture(scope="module")
+def orc(prec):
+    from oracle import oracle
+    return oracle.Oracle(prec)
+
+
+def _env(cfg, prec):
+    from tfmpc_b200 import envs
+    e = envs.make_env(cfg)
+    e.dtype = _dt(prec)
+    return e
+
+
+def test_native_library_is_loaded(prec):
+    """The CUDA extension must be the thing that runs: loaded from the in-tree .so, launching kernels."""
+    from tfmpc_b200 import _native, ops
+    lib = _native.load(prec)
+    before = _native.kernel_launch_count(prec)
+    H = torch.eye(2, device="cuda", dtype=_dt(prec))[None] * 2
+    z = torch.zeros(1, 2, device="cuda", dtype=_dt(prec))
+    ops.boxqp(H, z - 1, z - 1, z + 1, z)
+    torch.cuda.synchronize()
+    assert _native.kernel_launch_count(prec) == before + 1
+    assert lib.tfmpc_real_bytes() == (4 if prec == "f32" else 8)
+    with open("/proc/self/maps") as fh:
+        assert "libtfmpc_b200" in fh.read()
+
+
+def test_rejects_cpu_tensors(prec):
+    from tfmpc_b200 import _native, ops
+    H = torch.eye(2, dtype=_dt(prec))[None]
+    z = torch.zeros(1, 2, dtype=_dt(prec))
+    with pytest.raises(_native.TfmpcError):
+        ops.boxqp(H, z, z - 1, z + 1, z)
+
+
+# ------------------------------------------------------------------ LQR
+@pytest.mark.parametrize("name", golden_names("lqr_"))
+def test_lqr_golden(prec, name):
+    from tfmpc_b200.solvers.lqr import LQR
+    d = golden(name, prec)
+    T = int(d["T"])
+    solver = LQR(d["F"], d["f"], d["C"], d["c"], dtype=_dt(prec))
+    t = tol(prec, 2e-2 if name == "lqr_rand5" else 5e-5, 1e-9)
+    traj = solver.solve(d["x0"], T)
+    assert rel(traj.states, d["states"][..., 0]) < t
+    assert rel(traj.actions, d["actions"][..., 0]) < t
+    assert rel(traj.costs, d["costs"]) < t
+    policy, value_fn = solver.backward(T)
+    assert len(policy) == len(value_fn) == T
+    assert rel(np.stack([_np(K) for K, _ in policy]), d["K"]) < t
+    assert rel(np.stack([_np(k) for _, k in policy]), d["k"]) < t
+    assert rel(np.stack([_np(V) for V, _, _ in value_fn]), d["V"]) < t
+    assert rel(np.stack([float(c) for _, _, c in value_fn]), d["const"]) < t
+    # forward(policy, x0, T) reproduces the trajectory; transition/cost/final_cost agree with it (tests/test_lqr.py:51-76)
+    xs, us, cs = solver.forward(policy, d["x0"], T)
+    assert rel(_np(xs)[..., 0], d["states"][..., 0]) < t and rel(_np(cs), d["costs"]) < t
+    x1 = solver.transition(d["states"][0], d["actions"][0])
+    assert rel(_np(x1), d["states"][1]) < t
+    assert abs(float(solver.cost(d["states"][0], d["actions"][0])) - float(d["costs"][0])) < t * max(1, abs(float(d["costs"][0])))
+    assert abs(float(solver.final_cost(d["states"][-1])) - float(d["costs"][-1])) < t * max(1, abs(float(d["costs"][-1])))
+
+
+def test_lqr_batched_vs_oracle(prec, orc):
+    """BASELINE config C2 shape: shared F, f, C, per-problem c and x0 (navlin, beta = 5, H = 10)."""
+    from tfmpc_b200 import envs
+    rng = np.random.RandomState(0)
+    B, T = 4096, 10
+    goal = rng.uniform(-10, 10, size=(B, 2))
+    x0 = rng.normal(size=(B, 2))
+    solver = envs.make_lqr_linear_navigation(goal, 5.0)
+    solver.dtype = _dt(prec)
+    solver.__init__(solver.F, solver.f, solver.C, solver.c, dtype=_dt(prec))
+    out = solver.solve_device(x0, T, want_policy=True, want_value=True)
+    F = np.concatenate([np.eye(2), np.eye(2)], axis=1)
+    c = np.concatenate([-2 * goal, np.zeros_like(goal)], axis=1)
+    r = orc.lqr_solve(F, np.zeros(2), np.diag([2.0, 2.0, 10.0, 10.0]), c, x0, T)
+    t = tol(prec, 1e-5, 1e-12)
+    for key in ("states", "actions", "costs", "K", "k", "V", "v", "const"):
+        assert rel(_np(out[key]), r[key]) < t, key
+    assert int(out["status"].abs().sum()) == 0
+
+
+def test_lqr_generic_sizes_vs_oracle(prec, orc):
+    """Random problems of the sizes the reference's own test draws (tests/test_lqr.py:12-15: n, m in [2, 10)),
+    through the shared-memory warp kernel, including per-problem F, f, C, c."""
+    from tfmpc_b200 import ops
+    rng = np.random.RandomState(1)
+    for n, m, B in [(4, 3, 7), (9, 9, 5), (2, 7, 3), (16, 12, 2), (32, 32, 2)]:
+        N = n + m
+        A = rng.normal(size=(B, N, N))
+        C = A @ np.swapaxes(A, 1, 2) / N + np.eye(N)
+        F = rng.normal(size=(B, n, N)) / np.sqrt(N)
+        f, c, x0 = rng.normal(size=(B, n)), rng.normal(size=(B, N)), rng.normal(size=(B, n))
+        out = ops.lqr_solve(_cu(F, prec), _cu(f, prec), _cu(C, prec), _cu(c, prec), _cu(x0, prec), 8)
+        r = orc.lqr_solve(F, f, C, c, x0, 8)
+        t = tol(prec, 2e-4, 1e-10)
+        for key in ("states", "actions", "costs", "K", "V", "const"):
+            assert rel(_np(out[key]), r[key]) < t, (n, m, key)
+
+
+def test_lqr_readme_table(prec):
+    from tfmpc_b200 import envs
+    solver = envs.make_lqr_linear_navigation(np.array([[8.0], [-9.0]]), 5.0)
+    traj = solver.solve(np.zeros((2, 1)), 10, terminal_zero=True)
+    assert np.allclose(traj.final_state, [7.757592, -8.727291], atol=2e-5)
+    assert abs(traj.total_cost - (-1045.4086)) < 2e-3
+    assert "Trajectory(init=" in repr(traj) and "Steps" in str(traj)
+
+
+def test_lqr_host_buffer_entry_point(prec, orc):
+    from tfmpc_b200 import ops
+    rng = np.random.RandomState(2)
+    B, T = 257, 10
+    goal, x0 = rng.uniform(-10, 10, size=(B, 2)), rng.normal(size=(B, 2))
+    F = np.concatenate([np.eye(2), np.eye(2)], axis=1)
+    c = np.concatenate([-2 * goal, np.zeros_like(goal)], axis=1)
+    h = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=_dt(prec))  # noqa: E731
+    out = ops.lqr_solve_host(h(F), h(np.zeros(2)), h(np.diag([2.0, 2.0, 10.0, 10.0])), h(c), h(x0), T)
+    r = orc.lqr_solve(F, np.zeros(2), np.diag([2.0, 2.0, 10.0, 10.0]), c, x0, T)
+    assert not out["states"].is_cuda
+    assert rel(out["states"].numpy(), r["states"]) < tol(prec, 1e-5, 1e-12)
+    assert rel(out["costs"].numpy(), r["costs"]) < tol(prec, 1e-5, 1e-12)
+
+
+# ------------------------------------------------------------------ box-QP
+def test_boxqp_golden(prec):
+    from tfmpc_b200 import ops
+    d = golden("boxqp", prec)
+    for m in sorted(set(int(v) for v in d["dim"])):
+        idx = np.where(d["dim"] == m)[0]
+        out = ops.boxqp(_cu(d["H"][idx][:, :m, :m], prec), _cu(d["q"][idx][:, :m, 0], prec), _cu(d["low"][idx][:, :m, 0], prec),
+                        _cu(d["high"][idx][:, :m, 0], prec), _cu(d["x0"][idx][:, :m, 0], prec))
+        assert np.max(np.abs(_np(out["x"]) - d["x"][idx][:, :m, 0])) < tol(prec, 5e-6, 1e-12)
+        assert (_np(out["free"]) == (d["free"][idx][:, :m, 0] > 0)).all()
+        assert (_np(out["nfree"]) == d["nfree"][idx]).all()
+        Hf = _np(out["Hfree"])
+        for j, i in enumerate(idx):
+            nf = int(d["nfree"][i])
+            if nf:
+                assert np.max(np.abs(np.tril(Hf[j, :nf, :nf]) - np.tril(d["Hfree"][i, :nf, :nf]))) < tol(prec, 5e-6, 1e-12)
+
+
+def test_boxqp_random_vs_oracle(prec, orc):
+    from tfmpc_b200 import ops
+    rng = np.random.RandomState(3)
+    for m in (2, 3, 6):
+        B = 2000
+        A = rng.normal(size=(B, m, m))
+        H = A @ np.swapaxes(A, 1, 2) + 0.3 * np.eye(m)
+        q = rng.normal(size=(B, m)) * 3
+        lo, hi = -rng.uniform(0.05, 1.5, size=(B, m)), rng.uniform(0.05, 1.5, size=(B, m))
+        x0 = (lo + hi) / 2
+        out = ops.boxqp(_cu(H, prec), _cu(q, prec), _cu(lo, prec), _cu(hi, prec), _cu(x0, prec))
+        r = orc.boxqp(H, q, lo, hi, x0)
+        same = (_np(out["free"]) == r["free"]).all(axis=1)
+        assert same.mean() > tol(prec, 0.995, 0.9999)
+        assert np.max(np.abs(_np(out["x"]) - r["x"])[same]) < tol(prec, 2e-5, 1e-11)
+
+
+# ------------------------------------------------------------------ environments
+@pytest.mark.parametrize("name", golden_names("env_"))
+def test_env_ops_golden(prec, name):
+    d = golden(name, prec)
+    env = _env(cfg_of(d), prec)
+    x, u = d["x"], d["u"]
+    t = tol(prec, 3e-6, 1e-13)
+    assert rel(_np(env.transition(x, u, batch=True)), d["next"]) < t
+    assert rel(_np(env.cost(x, u, batch=True)), d["cost"]) < t
+    assert rel(_np(env.final_cost(x)), d["final_cost"]) < t
+    tm = env.get_linear_transition(x, u, batch=True)
+    cm = env.get_quadratic_cost(x, u, batch=True)
+    fm = env.get_quadratic_final_cost(x[-1])
+    assert tm.f.shape == d["f"].shape and tm.f_x.shape == d["f_x"].shape and cm.l_ux.shape == d["l_ux"].shape
+    for got, key in ((tm.f, "f"), (tm.f_x, "f_x"), (tm.f_u, "f_u"), (cm.l, "l"), (cm.l_x, "l_x"), (cm.l_u, "l_u"), (cm.l_xx, "l_xx"),
+                     (cm.l_uu, "l_uu"), (cm.l_ux, "l_ux"), (cm.l_xu, "l_xu"), (fm.l, "fl"), (fm.l_x, "fl_x"), (fm.l_xx, "fl_xx")):
+        assert np.max(np.abs(_np(got) - d[key])) < t * max(1.0, np.abs(d[key]).max()), key
+    # batched == unbatched (reference tests/test_diffenv.py:18-70)
+    one = env.get_linear_transition(x[0], u[0], batch=False)
+    assert np.allclose(_np(one.f_x), _np(tm.f_x[0])) and one.f.shape == (env.state_size, 1)
+
+
+# ------------------------------------------------------------------ iLQR stages
+@pytest.mark.parametrize("name", golden_names("stage_"))
+def test_ilqr_stages_golden(prec, name):
+    """start / derivatives / backward / forward with the reference's signatures (tests/test_ilqr.py:48-109)."""
+    from tfmpc_b200.solvers.ilqr import iLQR
+    d = golden(name, prec)
+    cfg = cfg_of(d)
+    env = _env(cfg, prec)
+    solver = iLQR(env, dtype=_dt(prec))
+    T = int(d["T"])
+    n, m = env.state_size, env.action_size
+    x, u, c = solver.start(d["x0"], T, u_init=d["u_init"])
+    assert tuple(x.shape) == (T + 1, n, 1) and tuple(u.shape) == (T, m, 1) and tuple(c.shape) == (T + 1,)
+    t = tol(prec, 3e-5, 1e-11)
+    assert rel(_np(x), d["states0"]) < t and rel(_np(c), d["costs0"]) < t
+    models = solver.derivatives(x, u)
+    assert len(models) == 3 and all(g.shape[0] == T for g in models[0]) and all(g.shape[0] == T for g in models[1])
+    reservoir = cfg["cls_name"] == "Reservoir"
+    for tag, mu in (("mu0", 0.0), ("mu1", 1.0), ("mu3", 1e-3)):
+        K, k, J, dV1, dV2 = solver.backward(T, u, *models, mu=mu)
+        assert tuple(K.shape) == (T, m, n) and tuple(k.shape) == (T, m, 1)
+        dk = np.abs(_np(k) - d["k_" + tag])
+        if reservoir:  # exact ties of the bang-bang rule: see tests/test_oracle_golden.py
+            flips = dk > 1e-3
+            assert np.all(np.abs(dk[flips] - 1.0) < 1e-5) and flips.mean() < 0.15
+            continue
+        assert dk.max() < t * max(1.0, np.abs(d["k_" + tag]).max())
+        assert np.max(np.abs(_np(K) - d["K_" + tag])) < t * max(1.0, np.abs(d["K_" + tag]).max())
+        for got, key in ((J, "J"), (dV1, "dV1"), (dV2, "dV2")):
+            ref = float(d[f"{key}_{tag}"])
+            assert abs(float(got) - ref) < t * max(1.0, abs(ref)) * 4, (key, tag)
+        if tag == "mu0":
+            K0, k0 = K, k
+    if reservoir:
+        return
+    for i in range(3):
+        xs, us, cs, J, res = solver.forward(x, u, K0, k0, float(d[f"alpha_{i}"]))
+        assert tuple(cs.shape) == (T + 1,)
+        assert rel(_np(xs), d[f"fx_{i}"]) < t and rel(_np(us), d[f"fu_{i}"]) < t and rel(_np(cs), d[f"fc_{i}"]) < t
+        assert abs(float(J) - float(d[f"fJ_{i}"])) < t * max(1.0, abs(float(d[f"fJ_{i}"]))) * 4
+        assert abs(float(res) - float(d[f"fres_{i}"])) < t * max(1.0, abs(float(d[f"fres_{i}"])))
+        # rollout self-consistency (tests/test_ilqr.py:92-109)
+        assert rel(_np(env.transition(xs[:-1], us, batch=True)), _np(xs[1:])) < t
+
+
+# ------------------------------------------------------------------ iLQR solve
+@pytest.mark.parametrize("name", [n for n in golden_names("solve_") if "res" not in n])
+def test_ilqr_solve_golden(prec, name):
+    """Same inputs as the reference run that produced the fixture: same iteration count, total cost within
+    1e-4 relative, actions within 1e-4."""
+    from tfmpc_b200.solvers.ilqr import iLQR
+    d = golden(name, prec)
+    env = _env(cfg_of(d), prec)
+    solver = iLQR(env, dtype=_dt(prec))
+    traj, its = solver.solve(d["x0"], int(d["T"]), u_init=d["u_init"])
+    tc, tg = traj.total_cost, d["costs"].sum(1)
+    assert np.all(np.abs(tc - tg) <= 1e-4 * np.abs(tg)), (tc, tg)
+    slack = 0 if prec == "f64" else 1
+    assert np.all(np.abs(np.asarray(its) - d["iterations"]) <= slack), (its, d["iterations"])
+    if np.all(np.asarray(its) == d["iterations"]):
+        assert np.max(np.abs(traj.actions - d["actions"])) < tol(prec, 2e-4, 1e-6)
+    # single-problem call returns the reference's types
+    t1, it1 = solver.solve(d["x0"][0], int(d["T"]), u_init=d["u_init"][0])
+    assert t1.states.shape == (int(d["T"]) + 1, env.state_size) and isinstance(it1, int)
+    assert abs(t1.total_cost - tc[0]) <= 1e-6 * abs(tc[0])
+
+
+def _batch_case(cfg, B, T, seed):
+    from tfmpc_b200.envs import synthetic
+    rng = np.random.RandomState(seed)
+    x0 = synthetic.sample_x0(cfg, B, rng)
+    c = cfg["config"]
+    if cfg["cls_name"] == "Navigation":
+        lo, hi = np.ravel(c["low"]), np.ravel(c["high"])
+    elif cfg["cls_name"] == "NavigationLQR":
+        n = len(c["goal"])
+        lo = np.full(n, c.get("low", -np.inf) if c.get("low") is not None else -np.inf)
+        hi = np.full(n, c.get("high", np.inf) if c.get("high") is not None else np.inf)
+    else:
+        lo, hi = np.zeros(x0.shape[1]), np.ones(x0.shape[1])
+    return x0, synthetic.sample_u_init(lo, hi, B, T, rng)
+
+
+def _solve_both(cfg, prec, orc, B, T, seed):
+    from tfmpc_b200.solvers.ilqr import iLQR
+    x0, u0 = _batch_case(cfg, B, T, seed)
+    solver = iLQR(_env(cfg, prec), dtype=_dt(prec))
+    out = solver.solve_device(x0, T, u_init=u0)
+    torch.cuda.synchronize()
+    g = {k: _np(v) for k, v in out.items()}
+    r = orc.ilqr_solve(orc.make_env(cfg), x0, u0)
+    return g, r
+
+
+@pytest.mark.parametrize("case", ["nav_h50", "nav_h12", "navlqr_box", "navlqr_free", "navlqr3_box"])
+def test_ilqr_solve_vs_oracle_small(prec, orc, case):
+    """Seeded random batches, CUDA vs oracle: iteration counts equal on >= 97% (fp32) / 99.5% (fp64) of the
+    problems and never more than +-1 apart beyond a 1% tail; converged cost within 1e-4 relative wherever the
+    counts agree."""
+    from tfmpc_b200.envs import synthetic
+    cfg, B, T = {
+        "nav_h50": (synthetic.navigation_config(), 2048, 50),
+        "nav_h12": (synthetic.navigation_config(), 512, 12),
+        "navlqr_box": (synthetic.navlqr_config([5.5, -9.0], 5.0, -1.0, 1.0), 512, 10),
+        "navlqr_free": (synthetic.navlqr_config([5.5, -9.0], 0.5), 512, 10),
+        "navlqr3_box": (synthetic.navlqr_config([1.0, -2.0, 3.0], 0.5, -0.4, 0.6), 512, 8),
+    }[case]
+    g, r = _solve_both(cfg, prec, orc, B, T, seed=11)
+    it_g, it_r = g["stats"][:, 0], r["iterations"]
+    same = it_g == it_r
+    assert same.mean() >= tol(prec, 0.97, 0.995), same.mean()
+    assert (np.abs(it_g - it_r) <= 1).mean() >= 0.99
+    tc_g, tc_r = g["costs"].sum(1), r["costs"].sum(1)
+    relc = np.abs(tc_g - tc_r) / np.abs(tc_r)
+    assert np.all(relc[same] <= 1e-4), relc[same].max()
+    assert np.max(np.abs(g["actions"] - r["actions"])[same]) < tol(prec, 5e-3, 1e-6)
+    assert (g["stats"][same, 1] == r["n_backward"][same]).mean() > 0.99
+    assert (g["stats"][same, 2] == r["n_rollouts"][same]).mean() > 0.97
+    assert (g["stats"][:, 3] == r["status"]).mean() > 0.99
+
+
+@pytest.mark.parametrize("case", ["hvac6", "hvac32", "res4", "res20"])
+def test_ilqr_solve_vs_oracle_large(prec, orc, case):
+    from tfmpc_b200.envs import synthetic
+    cfg, B, T = {
+        "hvac6": (synthetic.hvac_grid_config(2, 3), 64, 48),
+        "hvac32": (synthetic.hvac_grid_config(4, 8), 24, 48),
+        "res4": (synthetic.reservoir_config(4), 64, 40),
+        "res20": (synthetic.reservoir_config(20), 24, 40),
+    }[case]
+    g, r = _solve_both(cfg, prec, orc, B, T, seed=5)
+    assert (g["stats"][:, 3] == 0).all() and (r["status"] == 0).all()
+    tc_g, tc_r = g["costs"].sum(1), r["costs"].sum(1)
+    it_g, it_r = g["stats"][:, 0], r["iterations"]
+    if case.startswith("hvac"):
+        if prec == "f64":
+            assert (it_g == it_r).mean() >= 0.95
+            assert np.all((np.abs(tc_g - tc_r) / np.abs(tc_r))[it_g == it_r] <= 1e-6)
+        else:
+            # fp32 with costs ~1e7 (20000/deg penalty): summation-order noise decides late accept/reject ties
+            assert np.median(np.abs(tc_g - tc_r) / np.abs(tc_r)) <= 1e-4
+            assert np.all(np.abs(tc_g - tc_r) / np.abs(tc_r) <= 2e-2)
+            assert np.abs(it_g - it_r).mean() <= 10
+    else:  # Reservoir: distributional parity only
+        assert abs(np.mean(tc_g) - np.mean(tc_r)) <= 0.05 * abs(np.mean(tc_r))
+        assert abs(it_g.mean() - it_r.mean()) <= 0.35 * it_r.mean()
+    # every solution is a valid rollout of the env from x0 under its own actions, inside the action box
+    assert g["actions"].min() >= 0.0 and g["actions"].max() <= 1.0
+
+
+def test_ilqr_reproduces_lqr(prec):
+    """iLQR on unconstrained NavigationLQR == LQR (SURVEY 8(c) cross-pin): 2 outer iterations (index 1)."""
+    from tfmpc_b200 import envs
+    from tfmpc_b200.envs import synthetic
+    from tfmpc_b200.solvers.ilqr import iLQR
+    g = np.array([5.5, -9.0])
+    for beta in (0.5, 5.0):
+        env = _env(synthetic.navlqr_config(g, beta), prec)
+        traj, it = iLQR(env, dtype=_dt(prec)).solve(np.zeros((2, 1)), 10, seed=0)
+        lq = envs.make_lqr_linear_navigation(g.reshape(2, 1), beta)
+        lq.__init__(lq.F, lq.f, lq.C, lq.c, dtype=_dt(prec))
+        ref = lq.solve(np.zeros((2, 1)), 10)
+        assert it == 1
+        assert np.max(np.abs(traj.actions - ref.actions)) < tol(prec, 2e-4, 1e-9)
+        assert abs(traj.total_cost - (ref.total_cost + 11 * g @ g)) < tol(prec, 2e-2, 1e-8)
+
+
+def test_ilqr_host_buffer_entry_point(prec, orc):
+    from tfmpc_b200 import ops
+    from tfmpc_b200.envs import synthetic
+    cfg = synthetic.navigation_config()
+    x0, u0 = _batch_case(cfg, 300, 20, 4)
+    env = _env(cfg, prec)
+    h = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=_dt(prec))  # noqa: E731
+    out = ops.ilqr_solve_host(env.native(_dt(prec)), h(x0), h(u0))
+    r = orc.ilqr_solve(orc.make_env(cfg), x0, u0)
+    same = out["stats"][:, 0].numpy() == r["iterations"]
+    assert same.mean() > 0.97
+    relc = np.abs(out["costs"].numpy().sum(1) - r["costs"].sum(1)) / np.abs(r["costs"].sum(1))
+    assert np.all(relc[same] < 1e-4)
+
+
+# ------------------------------------------------------------------ full-size properties
+def test_full_size_nav_properties():
+    """BASELINE config C3 at full size (B = 65,536, H = 50), fp32: size-independent properties."""
+    from tfmpc_b200.envs import synthetic
+    from tfmpc_b200.solvers.ilqr import iLQR
+    cfg = synthetic.navigation_config()
+    B, T = 65536, 50
+    x0, u0 = _batch_case(cfg, B, T, 0)
+    env = _env(cfg, "f32")
+    solver = iLQR(env)
+    out = solver.solve_device(x0, T, u_init=u0)
+    torch.cuda.synchronize()
+    stats = out["stats"].cpu().numpy()
+    assert (stats[:, 3] == 0).mean() > 0.999          # converged
+    assert stats[:, 0].max() < 100 and 10 < stats[:, 0].mean() + 1 < 25   # mean 17.4
+    xs, us, cs = out["states"], out["actions"], out["costs"]
+    assert torch.all(us.abs() <= 1.0)
+    # the returned trajectory is a rollout of the env under the returned actions, with the returned costs
+    nxt = env.transition(xs[:, :-1].reshape(-1, 2), us.reshape(-1, 2), batch=True).reshape(B, T, 2)
+    assert torch.max((nxt - xs[:, 1:]).abs()) < 1e-4
+    assert torch.allclose(xs[:, 0], torch.as_tensor(x0, dtype=torch.float32, device="cuda"))
+    c = env.cost(xs[:, :-1].reshape(-1, 2), us.reshape(-1, 2), batch=True).reshape(B, T)
+    assert torch.max((c - cs[:, :-1]).abs() / (1 + c.abs())) < 1e-5
+    # iLQR never increases the cost of its starting rollout
+    s0, a0, c0 = solver.start(x0, T, u_init=u0)
+    assert torch.all(cs.sum(1) <= c0.sum(1) * (1 + 1e-5))
+    # idempotence: re-solving from the converged actions stops immediately with the same cost
+    out2 = solver.solve_device(x0, T, u_init=us)
+    st2 = out2["stats"].cpu().numpy()
+    assert (st2[:, 0] <= 1).mean() > 0.98
+    assert torch.max((out2["costs"].sum(1) - cs.sum(1)).abs() / cs.sum(1).abs()) < 1e-3
+    # permutation equivariance: problems are independent
+    perm = torch.randperm(B)
+    out3 = solver.solve_device(x0[perm.numpy()], T, u_init=u0[perm.numpy()])
+    assert torch.equal(out3["stats"][:, 0].cpu(), out["stats"][:, 0].cpu()[perm])
+    assert torch.equal(out3["costs"].cpu(), cs.cpu()[perm])
+
+
+def test_full_size_lqr_properties():
+    """BASELINE config C2 at full size (B = 65,536): Bellman consistency at every t (tests/test_lqr.py:78-86)."""
+    from tfmpc_b200 import envs
+    rng = np.random.RandomState(0)
+    B, T = 65536, 10
+    goal, x0 = rng.uniform(-10, 10, size=(B, 2)), rng.normal(size=(B, 2))
+    solver = envs.make_lqr_linear_navigation(goal, 5.0)
+    out = solver.solve_device(x0, T, want_policy=True, want_value=True)
+    x, costs, V, v, cst = out["states"].double(), out["costs"].double(), out["V"].double(), out["v"].double(), out["const"].double()
+    for t in range(T):
+        value = cst[:, t] + 0.5 * torch.einsum("bi,bij,bj->b", x[:, t], V[:, t], x[:, t]) + (v[:, t] * x[:, t]).sum(1)
+        togo = costs[:, t:].sum(1)
+        assert torch.max((value - togo).abs() / (1 + togo.abs())) < 1e-4
+    u = out["actions"].double()
+    assert torch.max((x[:, 1:] - (x[:, :-1] + u)).abs()) < 1e-4       # x' = x + u
+
+
+@pytest.mark.parametrize("case", ["res20", "hvac32"])
+def test_full_size_large_env_properties(case):
+    """BASELINE configs C4 / C5 (single solve) at a quarter of the full batch: rollout consistency and monotone cost."""
+    from tfmpc_b200.envs import synthetic
+    from tfmpc_b200.solvers.ilqr import iLQR
+    cfg, B, T = (synthetic.reservoir_config(20), 4096, 40) if case == "res20" else (synthetic.hvac_grid_config(4, 8), 4096, 48)
+    x0, u0 = _batch_case(cfg, B, T, 1)
+    env = _env(cfg, "f32")
+    solver = iLQR(env)
+    out = solver.solve_device(x0, T, u_init=u0)
+    torch.cuda.synchronize()
+    stats = out["stats"].cpu().numpy()
+    n = env.state_size
+    assert (stats[:, 3] == 0).all()
+    xs, us, cs = out["states"], out["actions"], out["costs"]
+    assert torch.all(us >= 0) and torch.all(us <= 1)
+    nxt = env.transition(xs[:, :-1].reshape(-1, n), us.reshape(-1, n), batch=True).reshape(B, T, n)
+    assert torch.max((nxt - xs[:, 1:]).abs() / (1 + xs[:, 1:].abs())) < 1e-5
+    s0, a0, c0 = solver.start(x0, T, u_init=u0)
+    assert torch.all(cs.sum(1) <= c0.sum(1) + 1e-5 * c0.sum(1).abs())

@@ -1,0 +1,129 @@
+// Shared definitions for the tfmpc_b200 CUDA sources (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/tfmpc_b200.h"
+
+typedef tfmpc_real real;
+
+#define MAXD TFMPC_MAX_DIM
+#define MAXZ TFMPC_MAX_ZONES
+#define N_ALPHA 11  // np.geomspace(1.0, alpha_min, 11), reference ilqr.py:322
+
+#ifdef __CUDACC__
+#define HD __host__ __device__ __forceinline__
+#else
+#define HD inline
+#endif
+
+// ---- scalar math in the build's precision (no fast-math: parity budget is 1e-4 after
+// ~50 steps x ~20 iterations; see DESIGN.md "numerics")
+HD real r_abs(real v) { return v < 0 ? -v : v; }
+HD real r_max(real a, real b) { return a > b ? a : b; }
+HD real r_min(real a, real b) { return a < b ? a : b; }
+HD real r_sgn(real v) { return (real)((v > 0) - (v < 0)); }
+HD real r_clip(real v, real lo, real hi) { return v < lo ? lo : (v > hi ? hi : v); }
+#ifdef TFMPC_F64
+HD real r_sqrt(real v) { return sqrt(v); }
+HD real r_exp(real v) { return exp(v); }
+HD real r_sin(real v) { return sin(v); }
+HD real r_cos(real v) { return cos(v); }
+#else
+HD real r_sqrt(real v) { return sqrtf(v); }
+HD real r_exp(real v) { return expf(v); }
+HD real r_sin(real v) { return sinf(v); }
+HD real r_cos(real v) { return cosf(v); }
+#endif
+
+// ---- environment parameters -------------------------------------------------------
+// Small environments (thread-per-problem kernels): passed by value as a kernel argument,
+// so every field is a constant-bank operand.
+struct EnvSmall {
+  int kind, n, m, nz, bounded;
+  real goal[4], low[4], high[4], beta;
+  real center[MAXZ][2], decay[MAXZ];
+};
+
+// Large environments (warp-per-problem kernels): one device blob, one row per lane.
+// Reservoir rows: cap lb ub lowpen highpen sppen rain | D[n][n] | Dt[n][n]
+// HVAC rows:      lb ub s(=1/cap) air_max g_out(=adj/R) g_hall t_out t_hall rowsum(A) | A[n][n] | Bt[n][n] (Bt[i][j] = s_j A[j][i])
+struct EnvLarge {
+  int kind, n, m;
+  const real *vec;   // [nvec][32] zero-padded
+  const real *matF;  // [32][32] row i = forward-matvec row of lane i, zero-padded
+  const real *matB;  // [32][32] row i = backward-matvec row of lane i, zero-padded
+};
+
+struct IlqrOpts {
+  real atol, c1;
+  int max_iterations;
+  double mu_min, delta_0;
+  real alphas[N_ALPHA];
+};
+
+struct tfmpc_env {
+  int kind, n, m, nz, bounded, small;
+  double low[MAXD], high[MAXD];
+  EnvSmall es;
+  EnvLarge el;
+  real *dblob;       // device storage behind el
+  int device;
+  // cached device scratch for the *_host entry points
+  void *h_scratch;
+  int64_t h_scratch_bytes;
+};
+
+// ---- error plumbing (api.cu) --------------------------------------------------------
+int tfmpc_set_error(int code, const char *fmt, ...);
+void tfmpc_count_launch(int n);
+#define CUDA_TRY(expr)                                                                         \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess) return tfmpc_set_error(TFMPC_E_CUDA, "%s: %s", #expr, cudaGetErrorString(_e)); \
+  } while (0)
+#define LAUNCH_CHECK()                                                                         \
+  do {                                                                                         \
+    tfmpc_count_launch(1);                                                                     \
+    cudaError_t _e = cudaGetLastError();                                                       \
+    if (_e != cudaSuccess) return tfmpc_set_error(TFMPC_E_CUDA, "kernel launch: %s", cudaGetErrorString(_e)); \
+  } while (0)
+
+// host launchers implemented per translation unit
+int small_ilqr_start(const tfmpc_env *e, int64_t B, int T, const real *x0, const real *u_init, real *states, real *actions,
+                     real *costs, cudaStream_t s);
+int small_ilqr_backward(const tfmpc_env *e, int64_t B, int T, const real *states, const real *actions, double mu, real *K, real *k,
+                        real *J, real *dV1, real *dV2, int32_t *status, cudaStream_t s);
+int small_ilqr_forward(const tfmpc_env *e, int64_t B, int T, const real *states, const real *actions, const real *K, const real *k,
+                       double alpha, real *xs, real *us, real *cs, real *J, real *residual, cudaStream_t s);
+int64_t small_ilqr_workspace_bytes(const tfmpc_env *e, int64_t B, int T);
+int small_ilqr_solve(const tfmpc_env *e, int64_t B, int T, const real *x0, const real *u_init, const IlqrOpts &o, real *states,
+                     real *actions, real *costs, int32_t *stats, void *ws, int64_t ws_bytes, cudaStream_t s);
+int small_boxqp(int64_t B, int m, const real *H, const real *q, const real *lo, const real *hi, real *x, real *Hfree, int32_t *isfree,
+                int32_t *nfree, int32_t *status, cudaStream_t s);
+
+int warp_ilqr_start(const tfmpc_env *e, int64_t B, int T, const real *x0, const real *u_init, real *states, real *actions,
+                    real *costs, cudaStream_t s);
+int warp_ilqr_backward(const tfmpc_env *e, int64_t B, int T, const real *states, const real *actions, double mu, real *K, real *k,
+                       real *J, real *dV1, real *dV2, int32_t *status, cudaStream_t s);
+int warp_ilqr_forward(const tfmpc_env *e, int64_t B, int T, const real *states, const real *actions, const real *K, const real *k,
+                      double alpha, real *xs, real *us, real *cs, real *J, real *residual, cudaStream_t s);
+int64_t warp_ilqr_workspace_bytes(const tfmpc_env *e, int64_t B, int T);
+int warp_ilqr_solve(const tfmpc_env *e, int64_t B, int T, const real *x0, const real *u_init, const IlqrOpts &o, real *states,
+                    real *actions, real *costs, int32_t *stats, void *ws, int64_t ws_bytes, cudaStream_t s);
+
+int env_ops_step(const tfmpc_env *e, int64_t R, const real *x, const real *u, real *xn, real *cost, cudaStream_t s);
+int env_ops_final_cost(const tfmpc_env *e, int64_t R, const real *x, real *cost, cudaStream_t s);
+int env_ops_linearize(const tfmpc_env *e, int64_t R, const real *x, const real *u, real *f_x, real *f_u, real *l, real *l_x,
+                      real *l_u, real *l_xx, real *l_uu, real *l_ux, real *l_xu, cudaStream_t s);
+int env_ops_final_quad(const tfmpc_env *e, int64_t R, const real *x, real *l, real *l_x, real *l_xx, cudaStream_t s);
+
+int lqr_solve_launch(int64_t B, int n, int m, int T, const real *F, int64_t sF, const real *f, int64_t sf, const real *C, int64_t sC,
+                     const real *c, int64_t sc, const real *x0, int terminal_zero, real *states, real *actions, real *costs,
+                     real *K, real *k, real *V, real *v, real *cst, int32_t *status, cudaStream_t s);
+int lqr_forward_launch(int64_t B, int n, int m, int T, const real *F, int64_t sF, const real *f, int64_t sf, const real *C, int64_t sC,
+                       const real *c, int64_t sc, const real *K, const real *k, const real *x0, real *states, real *actions, real *costs,
+                       cudaStream_t s);
+int lqr_step_launch(int64_t R, int n, int m, const real *F, int64_t sF, const real *f, int64_t sf, const real *C, int64_t sC, const real *c,
+                    int64_t sc, const real *x, const real *u, real *xn, real *cost, real *fcost, cudaStream_t s);

@@ -1,0 +1,597 @@
+// Per-problem iLQR building blocks for SMALL environments (n, m <= 4): everything lives in
+// registers of ONE thread.  Used by the thread-per-problem kernels in ilqr_small.cu.
+// All functions are __host__ __device__ so that tests/host_emulation can execute the very
+// same code on the CPU (a debugging aid for this GPU-less build container; the shipped
+// library contains no host path).
+//
+// Reference lines (relative to the reference repo root) are cited per block.
+#pragma once
+#include "common.cuh"
+
+template <int N, int M>
+struct Lin {  // TransitionApprox / CostApprox of tfmpc/envs/diffenv.py:6-8, one timestep
+  real f_x[N * N], f_u[N * M], l, l_x[N], l_u[M], l_xx[N * N], l_uu[M * M], l_xu[N * M];
+};
+
+// ------------------------------------------------------------------ environments
+// Navigation: tfmpc/envs/navigation/__init__.py:34-74
+HD real nav_lambda(const EnvSmall &e, const real *x, real *lam_z, real *r_z) {
+  real lam = (real)1;
+#pragma unroll
+  for (int z = 0; z < MAXZ; z++) {
+    if (z < e.nz) {
+      real d0 = x[0] - e.center[z][0], d1 = x[1] - e.center[z][1];
+      real r = r_sqrt(d0 * d0 + d1 * d1);
+      real l = (real)2 / ((real)1 + r_exp(-e.decay[z] * r)) - (real)1;
+      if (lam_z) { lam_z[z] = l; r_z[z] = r; }
+      lam *= l;
+    }
+  }
+  return lam;
+}
+
+template <int KIND, int N, int M>
+HD void env_step(const EnvSmall &e, const real *x, const real *u, real *xn) {
+  if (KIND == TFMPC_ENV_NAVLQR) {  // lqr/navigation/__init__.py:30-32
+#pragma unroll
+    for (int i = 0; i < N; i++) xn[i] = x[i] + u[i];
+  } else {  // navigation/__init__.py:34-48, cec=True
+    real lam = nav_lambda(e, x, nullptr, nullptr);
+#pragma unroll
+    for (int i = 0; i < N; i++) xn[i] = x[i] + lam * u[i];
+  }
+}
+
+template <int KIND, int N, int M>
+HD real env_cost(const EnvSmall &e, const real *x, const real *u) {
+  real c1 = 0;
+#pragma unroll
+  for (int i = 0; i < N; i++) c1 += (x[i] - e.goal[i]) * (x[i] - e.goal[i]);
+  if (KIND == TFMPC_ENV_NAVLQR) {  // lqr/navigation/__init__.py:34-41
+    real c2 = 0;
+#pragma unroll
+    for (int i = 0; i < M; i++) c2 += u[i] * u[i];
+    return c1 + e.beta * c2;
+  }
+  return c1;  // navigation/__init__.py:50-54 (no action cost)
+}
+
+template <int KIND, int N, int M>
+HD real env_final_cost(const EnvSmall &e, const real *x) {  // :43-47 / :56-60
+  real c1 = 0;
+#pragma unroll
+  for (int i = 0; i < N; i++) c1 += (x[i] - e.goal[i]) * (x[i] - e.goal[i]);
+  return c1;
+}
+
+// Analytic DiffEnv.get_linear_transition / get_quadratic_cost (diffenv.py:13-83); closed forms
+// pinned by the reference's tests/test_env_navigation.py:62-176 and test_env_lqr_navigation.py:28-135.
+template <int KIND, int N, int M>
+HD void env_linearize(const EnvSmall &e, const real *x, const real *u, Lin<N, M> &L) {
+#pragma unroll
+  for (int i = 0; i < N * N; i++) { L.f_x[i] = 0; L.l_xx[i] = 0; }
+#pragma unroll
+  for (int i = 0; i < N * M; i++) { L.f_u[i] = 0; L.l_xu[i] = 0; }
+#pragma unroll
+  for (int i = 0; i < M * M; i++) L.l_uu[i] = 0;
+  L.l = env_cost<KIND, N, M>(e, x, u);
+  if (KIND == TFMPC_ENV_NAVLQR) {
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      L.f_x[i * N + i] = 1; L.f_u[i * M + i] = 1;
+      L.l_x[i] = (real)2 * (x[i] - e.goal[i]); L.l_xx[i * N + i] = 2;
+    }
+#pragma unroll
+    for (int i = 0; i < M; i++) { L.l_u[i] = (real)2 * e.beta * u[i]; L.l_uu[i * M + i] = (real)2 * e.beta; }
+  } else {
+    real lam_z[MAXZ], r_z[MAXZ], g0 = 0, g1 = 0;
+    real lam = nav_lambda(e, x, lam_z, r_z);
+#pragma unroll
+    for (int z = 0; z < MAXZ; z++) {
+      if (z < e.nz) {
+        real ex = r_exp(-e.decay[z] * r_z[z]);  // d lambda_z / d r = 2 d e^{-dr} / (1 + e^{-dr})^2
+        real h = (real)2 * e.decay[z] * ex / (((real)1 + ex) * ((real)1 + ex));
+        real others = 1;
+#pragma unroll
+        for (int y = 0; y < MAXZ; y++)
+          if (y < e.nz && y != z) others *= lam_z[y];
+        g0 += h * (x[0] - e.center[z][0]) / r_z[z] * others;
+        g1 += h * (x[1] - e.center[z][1]) / r_z[z] * others;
+      }
+    }
+    // f_x = I + u (grad lambda)^T, f_u = lambda I
+    L.f_x[0] = (real)1 + u[0] * g0; L.f_x[1] = (real)0 + u[0] * g1;
+    L.f_x[2] = (real)0 + u[1] * g0; L.f_x[3] = (real)1 + u[1] * g1;
+    L.f_u[0] = lam; L.f_u[3] = lam;
+#pragma unroll
+    for (int i = 0; i < 2; i++) { L.l_x[i] = (real)2 * (x[i] - e.goal[i]); L.l_u[i] = 0; L.l_xx[i * 2 + i] = 2; }
+  }
+}
+
+template <int KIND, int N, int M>
+HD void env_final_quad(const EnvSmall &e, const real *x, real &l, real *l_x, real *l_xx) {  // diffenv.py:85-101
+  l = env_final_cost<KIND, N, M>(e, x);
+#pragma unroll
+  for (int i = 0; i < N * N; i++) l_xx[i] = 0;
+#pragma unroll
+  for (int i = 0; i < N; i++) { l_x[i] = (real)2 * (x[i] - e.goal[i]); l_xx[i * N + i] = 2; }
+}
+
+// ------------------------------------------------------------------ dense helpers (static indexing only)
+// Cholesky of the free block of H embedded in the full D x D matrix: clamped rows/columns are
+// replaced by identity rows, which leaves the free block's factor bit-identical to the factor
+// of the compacted H[free,free] while keeping every index compile-time (registers, no local
+// memory).  Failure rule = Eigen LLT / LAPACK potrf: a non-positive (or NaN) pivot.
+template <int D>
+HD int chol_masked(const real *H, const bool *fr, real *L) {
+#pragma unroll
+  for (int i = 0; i < D; i++)
+#pragma unroll
+    for (int j = 0; j < D; j++) L[i * D + j] = (fr[i] && fr[j]) ? H[i * D + j] : (i == j ? (real)1 : (real)0);
+  int fail = 0;
+#pragma unroll
+  for (int j = 0; j < D; j++) {
+    real s = L[j * D + j];
+#pragma unroll
+    for (int k = 0; k < j; k++) s -= L[j * D + k] * L[j * D + k];
+    if (!(s > 0)) { fail = 1; s = 1; }
+    real dj = r_sqrt(s);
+    L[j * D + j] = dj;
+#pragma unroll
+    for (int i = j + 1; i < D; i++) {
+      real t = L[i * D + j];
+#pragma unroll
+      for (int k = 0; k < j; k++) t -= L[i * D + k] * L[j * D + k];
+      L[i * D + j] = t / dj;
+    }
+  }
+  return fail;
+}
+
+template <int D>
+HD void chol_solve(const real *L, real *b) {  // L L^T y = b, in place
+#pragma unroll
+  for (int i = 0; i < D; i++) {
+    real s = b[i];
+#pragma unroll
+    for (int k = 0; k < i; k++) s -= L[i * D + k] * b[k];
+    b[i] = s / L[i * D + i];
+  }
+#pragma unroll
+  for (int i = D - 1; i >= 0; i--) {
+    real s = b[i];
+#pragma unroll
+    for (int k = i + 1; k < D; k++) s -= L[k * D + i] * b[k];
+    b[i] = s / L[i * D + i];
+  }
+}
+
+// ------------------------------------------------------------------ box-QP
+// tfmpc/utils/optimization.py:6-101 (projected_newton_qp) and :121-127 (_get_qp_indices).
+template <int M>
+HD real qp_value(const real *H, const real *q, const real *x) {  // :8-11
+  real quad = 0, lin = 0;
+#pragma unroll
+  for (int i = 0; i < M; i++) {
+    real hx = 0;
+#pragma unroll
+    for (int j = 0; j < M; j++) hx += H[i * M + j] * x[j];
+    quad += x[i] * hx;
+    lin += q[i] * x[i];
+  }
+  return (real)0.5 * quad + lin;
+}
+
+// x: in = start point, out = solution.  L: masked Cholesky factor of H[free,free].
+// fr: free flags at exit.  Returns 0, or 2 if a factorisation failed (:47-51).
+template <int M>
+HD int boxqp(const real *H, const real *q, const real *lo, const real *hi, real *x, real *L, bool *fr) {
+  const real rtol = (real)1e-8, armijo = (real)0.1, eps = (real)1e-6;
+  bool clamped[M];
+  real g[M], search[M], xc[M];
+#pragma unroll
+  for (int i = 0; i < M; i++) { clamped[i] = false; fr[i] = true; }
+  real value = qp_value<M>(H, q, x), old_value = 0;
+  int status = 0;
+  for (int it = 0; it < 100; it++) {
+    if (it > 0 && (old_value - value) < rtol * r_abs(old_value)) break;  // :27
+    old_value = value;
+    bool changed = false, allc = true;
+#pragma unroll
+    for (int i = 0; i < M; i++) {
+      real s = 0;
+#pragma unroll
+      for (int j = 0; j < M; j++) s += H[i * M + j] * x[j];
+      g[i] = q[i] + s;  // :34
+    }
+#pragma unroll
+    for (int i = 0; i < M; i++) {  // :121-127
+      bool c = (r_abs(x[i] - lo[i]) < eps && g[i] > 0) || (r_abs(hi[i] - x[i]) < eps && g[i] < 0);
+      changed = changed || (c != clamped[i]);
+      clamped[i] = c;
+      fr[i] = !c;
+      allc = allc && c;
+    }
+    if (it == 0 || changed) {  // :37-51
+      if (chol_masked<M>(H, fr, L)) { status = 2; break; }
+    }
+    if (allc) break;  // :53
+    real gn = 0;
+#pragma unroll
+    for (int i = 0; i < M; i++) gn += fr[i] ? g[i] * g[i] : (real)0;
+    if (r_sqrt(gn) < eps) break;  // :58-62
+    real rhs[M];
+#pragma unroll
+    for (int i = 0; i < M; i++) {  // grad_clamped = q + H (x * clamped), :65
+      real s = 0;
+#pragma unroll
+      for (int j = 0; j < M; j++) s += H[i * M + j] * (clamped[j] ? x[j] : (real)0);
+      rhs[i] = fr[i] ? q[i] + s : (real)0;
+    }
+    chol_solve<M>(L, rhs);
+    real sdotg = 0;
+#pragma unroll
+    for (int i = 0; i < M; i++) {
+      search[i] = fr[i] ? -rhs[i] - x[i] : (real)0;  // :70
+      sdotg += search[i] * g[i];
+    }
+    if (sdotg >= 0) break;  // :75-79
+    double step = 1.0;
+    real vc;
+    for (;;) {  // :82-95
+      real st = (real)step;
+#pragma unroll
+      for (int i = 0; i < M; i++) xc[i] = r_clip(x[i] + st * search[i], lo[i], hi[i]);
+      vc = qp_value<M>(H, q, xc);
+      if (!((vc - old_value) / (st * sdotg) < armijo)) break;
+      step *= 0.6;
+      if (step < 1e-22) {  // the reference evaluates xc, vc once more, then gives up
+        st = (real)step;
+#pragma unroll
+        for (int i = 0; i < M; i++) xc[i] = r_clip(x[i] + st * search[i], lo[i], hi[i]);
+        vc = qp_value<M>(H, q, xc);
+        break;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < M; i++) x[i] = xc[i];
+    value = vc;
+  }
+  return status;
+}
+
+// ------------------------------------------------------------------ iLQR backward, one timestep
+// tfmpc/solvers/ilqr.py:108-170 with the controllers of :357-387.  V_x, V_xx, J, dV1, dV2 are
+// carried across timesteps.  Returns 0, 1 (unconstrained Cholesky failed) or 2 (box-QP failed).
+template <int KIND, int N, int M>
+HD int backward_step(const EnvSmall &e, const Lin<N, M> &L, const real *u, real mu, real *V_x, real *V_xx, real &J, real &dV1,
+                     real &dV2, real *K, real *k) {
+  real Q_x[N], Q_u[M], Q_xx[N * N], Q_uu[M * M], Q_ux[M * N], Q_uu_reg[M * M], Q_ux_reg[M * N];
+  real fxTV[N * N], fuTV[M * N], fuTVr[M * N];
+  int status = 0;
+#pragma unroll
+  for (int i = 0; i < N; i++) {  // :122
+    real s = 0;
+#pragma unroll
+    for (int p = 0; p < N; p++) s += L.f_x[p * N + i] * V_x[p];
+    Q_x[i] = L.l_x[i] + s;
+  }
+#pragma unroll
+  for (int i = 0; i < M; i++) {  // :123
+    real s = 0;
+#pragma unroll
+    for (int p = 0; p < N; p++) s += L.f_u[p * M + i] * V_x[p];
+    Q_u[i] = L.l_u[i] + s;
+  }
+#pragma unroll
+  for (int i = 0; i < N; i++)
+#pragma unroll
+    for (int j = 0; j < N; j++) {  // :125
+      real s = 0;
+#pragma unroll
+      for (int p = 0; p < N; p++) s += L.f_x[p * N + i] * V_xx[p * N + j];
+      fxTV[i * N + j] = s;
+    }
+#pragma unroll
+  for (int i = 0; i < M; i++)
+#pragma unroll
+    for (int j = 0; j < N; j++) {  // :126-127
+      real s = 0, sr = 0;
+#pragma unroll
+      for (int p = 0; p < N; p++) {
+        s += L.f_u[p * M + i] * V_xx[p * N + j];
+        sr += L.f_u[p * M + i] * (p == j ? V_xx[p * N + j] + mu * (real)1 : V_xx[p * N + j]);
+      }
+      fuTV[i * N + j] = s;
+      fuTVr[i * N + j] = sr;
+    }
+#pragma unroll
+  for (int i = 0; i < N; i++)
+#pragma unroll
+    for (int j = 0; j < N; j++) {  // :129
+      real s = 0;
+#pragma unroll
+      for (int p = 0; p < N; p++) s += fxTV[i * N + p] * L.f_x[p * N + j];
+      Q_xx[i * N + j] = L.l_xx[i * N + j] + s;
+    }
+#pragma unroll
+  for (int i = 0; i < M; i++) {
+#pragma unroll
+    for (int j = 0; j < M; j++) {  // :130, :133
+      real s = 0, sr = 0;
+#pragma unroll
+      for (int p = 0; p < N; p++) { s += fuTV[i * N + p] * L.f_u[p * M + j]; sr += fuTVr[i * N + p] * L.f_u[p * M + j]; }
+      Q_uu[i * M + j] = L.l_uu[i * M + j] + s;
+      Q_uu_reg[i * M + j] = L.l_uu[i * M + j] + sr;
+    }
+#pragma unroll
+    for (int j = 0; j < N; j++) {  // :131, :134 (l_xu^T)
+      real s = 0, sr = 0;
+#pragma unroll
+      for (int p = 0; p < N; p++) { s += fuTV[i * N + p] * L.f_x[p * N + j]; sr += fuTVr[i * N + p] * L.f_x[p * N + j]; }
+      Q_ux[i * N + j] = L.l_xu[j * M + i] + s;
+      Q_ux_reg[i * N + j] = L.l_xu[j * M + i] + sr;
+    }
+  }
+  if (e.bounded) {  // :136
+    bool any_nz = false;
+#pragma unroll
+    for (int i = 0; i < N * N; i++) any_nz = any_nz || (V_xx[i] != 0);
+    if (any_nz) {  // :137-138 -> _get_constrained_controller :364-387
+      real lo[M], hi[M], Lf[M * M];
+      bool fr[M];
+#pragma unroll
+      for (int i = 0; i < M; i++) { lo[i] = e.low[i] - u[i]; hi[i] = e.high[i] - u[i]; k[i] = (lo[i] + hi[i]) / (real)2; }
+      int st = boxqp<M>(Q_uu_reg, Q_u, lo, hi, k, Lf, fr);
+      if (st) status = 2;
+#pragma unroll
+      for (int j = 0; j < N; j++) {  // K[free] = -cholesky_solve(Hfree, Q_ux_reg[free]); clamped rows 0
+        real col[M];
+#pragma unroll
+        for (int i = 0; i < M; i++) col[i] = (fr[i] && !st) ? Q_ux_reg[i * N + j] : (real)0;
+        chol_solve<M>(Lf, col);
+#pragma unroll
+        for (int i = 0; i < M; i++) K[i * N + j] = (fr[i] && !st) ? -col[i] : (real)0;
+      }
+    } else {  // :139-141 bang-bang
+#pragma unroll
+      for (int i = 0; i < M * N; i++) K[i] = 0;
+#pragma unroll
+      for (int i = 0; i < M; i++) k[i] = (Q_u[i] >= 0) ? e.low[i] - u[i] : e.high[i] - u[i];
+    }
+  } else {  // :143 -> _get_unconstrained_controller :357-362
+    real R[M * M];
+    bool all[M];
+#pragma unroll
+    for (int i = 0; i < M; i++) all[i] = true;
+    if (chol_masked<M>(Q_uu_reg, all, R)) return 1;
+#pragma unroll
+    for (int i = 0; i < M; i++) k[i] = Q_u[i];
+    chol_solve<M>(R, k);
+#pragma unroll
+    for (int i = 0; i < M; i++) k[i] = -k[i];
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+      real col[M];
+#pragma unroll
+      for (int i = 0; i < M; i++) col[i] = Q_ux_reg[i * N + j];
+      chol_solve<M>(R, col);
+#pragma unroll
+      for (int i = 0; i < M; i++) K[i * N + j] = -col[i];
+    }
+  }
+  // value update with the UNregularised Q, :145-162
+  real KtQuu[N * M];
+#pragma unroll
+  for (int i = 0; i < N; i++)
+#pragma unroll
+    for (int j = 0; j < M; j++) {
+      real s = 0;
+#pragma unroll
+      for (int p = 0; p < M; p++) s += K[p * N + i] * Q_uu[p * M + j];
+      KtQuu[i * M + j] = s;
+    }
+  real Vn[N * N];
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    real a1 = 0, a2 = 0, a3 = 0;
+#pragma unroll
+    for (int p = 0; p < M; p++) { a1 += Q_ux[p * N + i] * k[p]; a2 += K[p * N + i] * Q_u[p]; a3 += KtQuu[i * M + p] * k[p]; }
+    V_x[i] = Q_x[i] + a1 + a2 + a3;
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+      real b1 = 0, b2 = 0, b3 = 0;
+#pragma unroll
+      for (int p = 0; p < M; p++) { b1 += Q_ux[p * N + i] * K[p * N + j]; b2 += K[p * N + i] * Q_ux[p * N + j]; b3 += KtQuu[i * M + p] * K[p * N + j]; }
+      Vn[i * N + j] = Q_xx[i * N + j] + b1 + b2 + b3;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < N; i++)
+#pragma unroll
+    for (int j = 0; j < N; j++) V_xx[i * N + j] = (real)0.5 * (Vn[i * N + j] + Vn[j * N + i]);  // :162
+  J += L.l;  // :164
+  real d1 = 0, d2 = 0;
+#pragma unroll
+  for (int i = 0; i < M; i++) d1 += k[i] * Q_u[i];
+  dV1 += d1;  // :166
+#pragma unroll
+  for (int j = 0; j < M; j++) {
+    real s = 0;
+#pragma unroll
+    for (int i = 0; i < M; i++) s += k[i] * Q_uu[i * M + j];
+    d2 += s * k[j];
+  }
+  dV2 += (real)0.5 * d2;  // :167
+  return status;
+}
+
+// ------------------------------------------------------------------ strided views
+// A problem's arrays are addressed as base[row * stride]: stride 1 = the reference's dense
+// [T, n] layout of one problem; stride S = struct-of-arrays workspace with the problem (slot)
+// index fastest, so that the 32 lanes of a warp touch 32 consecutive words.
+struct View {
+  real *p;
+  int64_t stride;
+  HD real &operator()(int row) const { return p[(int64_t)row * stride]; }
+};
+struct CView {
+  const real *p;
+  int64_t stride;
+  HD real operator()(int row) const { return p[(int64_t)row * stride]; }
+};
+
+// iLQR.backward over the whole horizon (ilqr.py:94-172), linearisation fused (ilqr.py:84-92).
+// Also accumulates sum_t max_i |k|/(|u|+1) for the g_norm test of ilqr.py:243.
+template <int KIND, int N, int M, class XV, class UV>
+HD int backward_pass(const EnvSmall &e, int T, const XV &X, const UV &U, real mu, const View &Kv, const View &kv, real &J, real &dV1,
+                     real &dV2, real &gsum) {
+  real V_x[N], V_xx[N * N], x[N], u[M];
+#pragma unroll
+  for (int i = 0; i < N; i++) x[i] = X(T * N + i);
+  env_final_quad<KIND, N, M>(e, x, J, V_x, V_xx);  // :101-104
+  dV1 = 0; dV2 = 0; gsum = 0;
+  int status = 0;
+  real xn[N], un[M];
+#pragma unroll
+  for (int i = 0; i < N; i++) xn[i] = X((T - 1) * N + i);
+#pragma unroll
+  for (int i = 0; i < M; i++) un[i] = U((T - 1) * M + i);
+  for (int t = T - 1; t >= 0; t--) {
+#pragma unroll
+    for (int i = 0; i < N; i++) x[i] = xn[i];
+#pragma unroll
+    for (int i = 0; i < M; i++) u[i] = un[i];
+    if (t > 0) {  // software prefetch of the next (earlier) timestep
+#pragma unroll
+      for (int i = 0; i < N; i++) xn[i] = X((t - 1) * N + i);
+#pragma unroll
+      for (int i = 0; i < M; i++) un[i] = U((t - 1) * M + i);
+    }
+    Lin<N, M> L;
+    env_linearize<KIND, N, M>(e, x, u, L);
+    real K[M * N], k[M];
+    int st = backward_step<KIND, N, M>(e, L, u, mu, V_x, V_xx, J, dV1, dV2, K, k);
+    if (st == 1) return 1;
+    if (st) status = st;
+    real mx = 0;
+#pragma unroll
+    for (int i = 0; i < M; i++) {
+      real v = r_abs(k[i]) / (r_abs(u[i]) + (real)1.0);
+      mx = (i == 0 || v > mx) ? v : mx;
+      kv(t * M + i) = k[i];
+    }
+    gsum += mx;
+#pragma unroll
+    for (int i = 0; i < M * N; i++) Kv(t * M * N + i) = K[i];
+  }
+  return status;
+}
+
+// iLQR.forward (ilqr.py:174-212).  cs may be a null view (p == nullptr) when costs are not wanted.
+template <int KIND, int N, int M, class XV, class UV, class KV>
+HD void forward_pass(const EnvSmall &e, int T, const XV &Xh, const UV &Uh, const KV &Kv, const KV &kv, real alpha, const View &Xo,
+                     const View &Uo, const View &Co, real &J, real &residual) {
+  real x[N], u[M], xn[N];
+  J = 0; residual = 0;
+#pragma unroll
+  for (int i = 0; i < N; i++) { x[i] = Xh(i); Xo(i) = x[i]; }
+  for (int t = 0; t < T; t++) {
+#pragma unroll
+    for (int i = 0; i < M; i++) {
+      real s = 0;
+#pragma unroll
+      for (int j = 0; j < N; j++) s += Kv(t * M * N + i * N + j) * (x[j] - Xh(t * N + j));
+      real du = alpha * kv(t * M + i) + s;            // :194
+      u[i] = r_clip(Uh(t * M + i) + du, e.low[i], e.high[i]);  // :196-197
+      residual = r_max(residual, r_abs(du));          // :206 (pre-clip)
+      Uo(t * M + i) = u[i];
+    }
+    real c = env_cost<KIND, N, M>(e, x, u);
+    env_step<KIND, N, M>(e, x, u, xn);
+    if (Co.p) Co(t) = c;
+    J += c;
+#pragma unroll
+    for (int i = 0; i < N; i++) { x[i] = xn[i]; Xo((t + 1) * N + i) = x[i]; }
+  }
+  real cf = env_final_cost<KIND, N, M>(e, x);
+  if (Co.p) Co(T) = cf;
+  J += cf;
+}
+
+// iLQR.start with pinned actions (ilqr.py:53-82)
+template <int KIND, int N, int M, class UV>
+HD void start_pass(const EnvSmall &e, int T, const real *x0, const UV &Ui, const View &Xo, const View &Uo, const View &Co) {
+  real x[N], u[M], xn[N];
+#pragma unroll
+  for (int i = 0; i < N; i++) { x[i] = x0[i]; Xo(i) = x[i]; }
+  for (int t = 0; t < T; t++) {
+#pragma unroll
+    for (int i = 0; i < M; i++) { u[i] = Ui(t * M + i); Uo(t * M + i) = u[i]; }
+    if (Co.p) Co(t) = env_cost<KIND, N, M>(e, x, u);
+    env_step<KIND, N, M>(e, x, u, xn);
+#pragma unroll
+    for (int i = 0; i < N; i++) { x[i] = xn[i]; Xo((t + 1) * N + i) = x[i]; }
+  }
+  if (Co.p) Co(T) = env_final_cost<KIND, N, M>(e, x);
+}
+
+// ------------------------------------------------------------------ whole solve, one problem
+// iLQR.solve (ilqr.py:214-283) + _backward (:285-315) + _forward (:317-355).  The nominal and
+// candidate trajectories ping-pong between two (X, U) buffer pairs; `cur` is the pair holding
+// the nominal at exit.  stats = {iteration index, backward passes, rollouts, status}.
+template <int KIND, int N, int M>
+HD int solve_one(const EnvSmall &e, const IlqrOpts &o, int T, const View X[2], const View U[2], const View &Kv, const View &kv,
+                 int32_t *stats) {
+  double mu = 0.0, delta = 1.0;  // python floats in the reference, ilqr.py:215-216
+  int cur = 0, n_bwd = 0, n_fwd = 0, status = TFMPC_ST_MAXITER, iteration = 0;
+  const View none = {nullptr, 0};
+  for (iteration = 0; iteration < o.max_iterations; iteration++) {
+    bool converged = false;
+    int guard = 0;
+    for (;;) {
+      real J_hat, dV1, dV2, gsum;
+      double mu_l = mu, delta_l = delta;  // _backward's bump is local, ilqr.py:308-309,315
+      int bst, tries = 0;
+      for (;;) {
+        bst = backward_pass<KIND, N, M>(e, T, X[cur], U[cur], (real)mu_l, Kv, kv, J_hat, dV1, dV2, gsum);
+        n_bwd++;
+        if (bst != 1 || ++tries > 200) break;
+        delta_l = fmax(o.delta_0, delta_l * o.delta_0);
+        mu_l = fmax(o.mu_min, mu_l * delta_l);
+      }
+      if (bst) { status = TFMPC_ST_NONPD; converged = true; break; }
+      real g = gsum / (real)T;  // :243
+      if (!(g == g)) { status = TFMPC_ST_NAN; converged = true; break; }
+      if (g < o.atol) { status = TFMPC_ST_CONVERGED; converged = true; break; }  // :245-248
+      bool accept = false;
+      real residual = 0;
+      for (int ai = 0; ai < N_ALPHA; ai++) {  // :322
+        real alpha = o.alphas[ai], J;
+        forward_pass<KIND, N, M>(e, T, X[cur], U[cur], Kv, kv, alpha, X[cur ^ 1], U[cur ^ 1], none, J, residual);
+        n_fwd++;
+        real delta_J = -alpha * (dV1 + alpha * dV2);  // :339
+        real dcost = J_hat - J;
+        real z = (delta_J > 0) ? dcost / delta_J : r_sgn(dcost);  // :342-346
+        if (z >= o.c1) { accept = true; break; }  // :351
+      }
+      if (residual < o.atol) {  // :253-257 (the candidate is taken even if it was rejected)
+        status = TFMPC_ST_CONVERGED; converged = true; cur ^= 1;
+        break;
+      }
+      if (accept) {  // :259-266
+        delta = fmin(1.0 / o.delta_0, delta / o.delta_0);
+        mu = mu * delta * (double)(mu * delta > o.mu_min);
+        cur ^= 1;
+        break;
+      }
+      delta = fmax(o.delta_0, delta * o.delta_0);  // :267-270
+      mu = fmax(o.mu_min, mu * delta);
+      if (++guard > 200) { status = TFMPC_ST_REGLOOP; converged = true; break; }
+    }
+    if (converged) break;
+  }
+  if (iteration >= o.max_iterations) iteration = o.max_iterations - 1;
+  stats[0] = iteration; stats[1] = n_bwd; stats[2] = n_fwd; stats[3] = status;
+  return cur;
+}

@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the batched iLQR hot path (BASELINE.json: "batched iLQR
+problem-iterations/sec at 1/2/4/8 B200 vs TF CPU ref").
+
+    python bench.py --gpus 1 --steps 5 --warmup 3                      # this repo's CUDA path
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+           bench.py --gpus N --steps K --warmup W                      # N GPUs, one rank per GPU
+    python bench.py --impl reference --steps 2 --warmup 1              # the CPU arm (oracle port, all host cores)
+
+A "step" is one pass of the hot path over one batch: iLQR.solve of B independent problems to convergence
+(reference tfmpc/solvers/ilqr.py:214-283 per problem).  The metric counts problem-iterations = passes of
+the reference's outer loop ilqr.py:227-277 (linearise + >= 1 backward pass + line search), summed over
+problems.  Workload (default): BASELINE config C3 -- nonlinear 2-D navigation with two deceleration zones,
+H = 50, B = 65,536 problems PER GPU (weak scaling: the batch is sharded, no data-path collective; with
+N > 1 ranks the per-problem costs and iteration counts are all-gathered once per step over NCCL).
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (description, batch per GPU, horizon)
+    "c3": ("C3 iLQR nonlinear navigation (nav.config.json, 2 zones, actions in [-1,1]) H=50", 65536, 50),
+    "c4": ("C4 iLQR reservoir control, 20 reservoirs, H=40", 16384, 40),
+    "c5s": ("C5 (single solve) iLQR HVAC 32 rooms 4x8 grid, H=48", 16384, 48),
+}
+
+
+def workload_cfg(name):
+    from tfmpc_b200.envs import synthetic
+    return {"c3": synthetic.navigation_config, "c4": lambda: synthetic.reservoir_config(20),
+            "c5s": lambda: synthetic.hvac_grid_config(4, 8)}[name]()
+
+
+def make_inputs(cfg, B, T, seed):
+    from tfmpc_b200.envs import synthetic
+    rng = np.random.RandomState(seed)
+    x0 = synthetic.sample_x0(cfg, B, rng).astype(np.float32)
+    if cfg["cls_name"] == "Navigation":
+        lo, hi = np.ravel(cfg["config"]["low"]), np.ravel(cfg["config"]["high"])
+    else:
+        lo, hi = np.zeros(x0.shape[1]), np.ones(x0.shape[1])
+    u0 = synthetic.sample_u_init(lo, hi, B, T, rng).astype(np.float32)
+    return np.ascontiguousarray(x0), np.ascontiguousarray(u0)
+
+
+# algorithmic work per problem-iteration, SURVEY.md section 8(d) / DESIGN.md "roofline":
+#   FLOPs = H * (lin_env * iterations + bwd * backward passes + fwd * reference-semantics rollouts)
+#   bytes = 4 * [(H(n+m)+n) read nominal + ((H+1)n + Hm + H+1) write candidate]  per problem-iteration (fused)
+def algorithmic_work(name, T, stats):
+    its = stats[:, 0].astype(np.float64) + 1.0
+    nb, nf = stats[:, 1].astype(np.float64), stats[:, 2].astype(np.float64)
+    if name == "c3":
+        n = m = 2
+        lin, bwd, fwd = 80.0, 329.0 + 100.0, 2 * m * n + 8 * m + n + 1 + 32.0
+    elif name == "c4":
+        n = m = 20
+        lin, bwd, fwd = 12.0 * n, 2.0 * n * n + 2 * n * m + 5 * m, 8 * m + n + 1 + 2.0 * n * n + 21 * n
+    else:
+        n = m = 32
+        lin, bwd, fwd = 6.0 * n, 2.0 * n * n + 2 * n * m + 5 * m, 8 * m + n + 1 + 3.0 * n * n + 25 * n
+    flops = T * (lin * its + bwd * nb + fwd * nf)
+    byts = 4.0 * ((T * (n + m) + n) + ((T + 1) * n + T * m + T + 1)) * its
+    return float(flops.sum()), float(byts.sum())
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for ts, r in self.rows if t0 - 0.05 <= ts <= t1 + 0.15] or [r for _, r in self.rows]
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            f = [x.strip() for x in r.split(",")]
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except (ValueError, IndexError):
+                continue
+            for nme, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        if not sm:
+            return None
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return json.load(fh), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+def cpu_baseline(name, T, sample, threads=0, repeats=1):
+    """The CPU arm: the oracle port (C, OpenMP over problems) on the host cores, on a bounded sample of the
+    same workload.  Returns (problem-iterations/s, cores, problem-iterations, seconds)."""
+    from oracle import oracle
+    o = oracle.Oracle("f32")
+    cfg = workload_cfg(name)
+    x0, u0 = make_inputs(cfg, sample, T, seed=12345)
+    env = o.make_env(cfg)
+    cores = o.max_threads() if threads <= 0 else threads
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        r = o.ilqr_solve(env, x0, u0, nthreads=cores)
+        dt = time.perf_counter() - t0
+        pi = float((r["iterations"] + 1).sum())
+        if best is None or dt < best[1]:
+            best = (pi, dt)
+    return best[0] / best[1], cores, best[0], best[1]
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    desc, _, T = WORKLOADS[args.workload]
+    sample = args.cpu_sample or {"c3": 65536, "c4": 512, "c5s": 128}[args.workload]
+    for _ in range(args.warmup):
+        cpu_baseline(args.workload, T, max(64, sample // 8))
+    vals, secs, pis = [], 0.0, 0.0
+    for _ in range(args.steps):
+        v, cores, pi, dt = cpu_baseline(args.workload, T, sample)
+        vals.append(v); secs += dt; pis += pi
+    value = pis / secs
+    line = {"impl": "reference", "metric": "batched iLQR problem-iterations/sec", "value": value, "unit": "problem-iterations/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "batch_per_step": sample, "horizon": T,
+                       "note": "CPU arm = this repo's C/OpenMP restatement of the reference algorithm (oracle/); the TensorFlow "
+                               "reference itself is not installable offline"},
+            "cpu_baseline": {"value": value, "unit": "problem-iterations/s", "cores": cores, "kind": "port",
+                             "sample": f"{sample} problems of the workload per step, {args.steps} steps"},
+            "e2e": {"value": value, "unit": "problem-iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from tfmpc_b200 import _native, envs, ops
+    from tfmpc_b200.solvers.ilqr import iLQR
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    desc, B, T = WORKLOADS[args.workload]
+    if args.batch:
+        B = args.batch
+    cfg = workload_cfg(args.workload)
+    env = envs.make_env(cfg)
+    solver = iLQR(env)
+    n, m = env.state_size, env.action_size
+    x0_h, u0_h = make_inputs(cfg, B, T, seed=1000 + rank)
+    x0_pin, u0_pin = torch.from_numpy(x0_h).pin_memory(), torch.from_numpy(u0_h).pin_memory()
+    x0, u0 = x0_pin.to(dev), u0_pin.to(dev)
+    out = {"states": torch.empty(B, T + 1, n, device=dev), "actions": torch.empty(B, T, m, device=dev),
+           "costs": torch.empty(B, T + 1, device=dev), "stats": torch.empty(B, 4, dtype=torch.int32, device=dev)}
+    nat, opts = env.native(), solver._opts()
+    gathered = [torch.empty(B, device=dev) for _ in range(world)] if world > 1 else None
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)   # 256 MB > 126 MB L2
+
+    def step():
+        ops.ilqr_solve(nat, x0, u0, opts, out)
+        if world > 1:   # the one collective of the sharded solve: per-problem total costs to every rank
+            dist.all_gather(gathered, out["costs"].sum(1))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    launches0 = _native.kernel_launch_count("f32")
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    t_wall0 = time.time()
+    for s in range(args.steps):
+        flush.zero_()                      # evict L2 between timed iterations (not timed)
+        ev[s][0].record()
+        step()
+        ev[s][1].record()
+    barrier()
+    t_wall1 = time.time()
+    launches = _native.kernel_launch_count("f32") - launches0
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = float(sum(step_ms))
+    stats = out["stats"].cpu().numpy()
+    pi_local = float((stats[:, 0] + 1).sum())
+    t = torch.tensor([total_ms, pi_local], dtype=torch.float64, device=dev)
+    if world > 1:
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        total_ms, pi_all = float(tmax[0]), float(tsum[1])
+    else:
+        pi_all = pi_local
+    value = pi_all * args.steps / (total_ms * 1e-3)
+
+    # ---- end to end through the public host-buffer API (pinned inputs -> results on the host), every rank
+    e2e_steps = max(1, min(args.steps, 3))
+    out_h = {"states": torch.empty(B, T + 1, n).pin_memory(), "actions": torch.empty(B, T, m).pin_memory(),
+             "costs": torch.empty(B, T + 1).pin_memory(), "stats": torch.empty(B, 4, dtype=torch.int32).pin_memory()}
+    ops.ilqr_solve_host(nat, x0_pin, u0_pin, opts, out_h)   # warm (allocates the cached device scratch)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ops.ilqr_solve_host(nat, x0_pin, u0_pin, opts, out_h)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = pi_all * e2e_steps / float(te[0])
+    h2d = x0_pin.numel() * 4 + u0_pin.numel() * 4
+    d2h = sum(v.numel() * 4 for v in out_h.values())
+
+    if rank == 0:
+        peaks, peak_src = measured_peaks()
+        lib = _native.load("f32")
+        tf, kms = ctypes.c_double(), ctypes.c_double()
+        lib.tfmpc_measure_fp32_peak(ctypes.byref(tf), ctypes.byref(kms))
+        flops, byts = algorithmic_work(args.workload, T, stats)
+        kernel_s = total_ms * 1e-3 / args.steps            # one solve kernel per step dominates the step
+        ach_tf, ach_gb = flops / kernel_s / 1e12, byts / kernel_s / 1e9
+        fp32 = {"bound": "fp32", "achieved": ach_tf, "peak": tf.value, "unit": "TFLOP/s", "frac": ach_tf / tf.value if tf.value else None,
+                "traffic": None, "peak_source": "FP32 FMA microbenchmark run in this process (tfmpc_measure_fp32_peak); nominal 148 SM x 128 lanes x 2 x clock"}
+        hbm = {"bound": "hbm", "achieved": ach_gb, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach_gb / peaks["hbm_gbs"], "traffic": None,
+               "peak_source": peak_src}
+        primary = fp32 if (fp32["frac"] or 0) >= hbm["frac"] else hbm
+        roofline = dict(primary)
+        roofline["kernel"] = "k_solve (thread-per-problem)" if args.workload == "c3" else "kw_solve (lane-per-state)"
+        roofline["algorithmic_flops_per_launch"] = flops
+        roofline["algorithmic_bytes_per_launch"] = byts
+        roofline["other"] = hbm if primary is fp32 else fp32
+        line = {"metric": "batched iLQR problem-iterations/sec", "value": value, "unit": "problem-iterations/s", "n_gpus": world,
+                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": desc, "batch_per_gpu": B, "global_batch": B * world, "horizon": T, "state_dim": n, "action_dim": m,
+                           "parallelism": f"batch sharded over {world} GPU(s), no data-path collective"
+                                          + ("; one NCCL all-gather of per-problem costs per step" if world > 1 else ""),
+                           "solver": "reference defaults atol=5e-3 max_iterations=100 mu_min=1e-6 delta_0=2 c1=0 alpha_min=1e-3",
+                           "l2": "256 MB buffer written between timed iterations (L2 flush, untimed); per-step working set 250 MB > 126 MB L2",
+                           "mean_iterations_per_solve": float((stats[:, 0] + 1).mean()),
+                           "problems_per_s": B * world * args.steps / (total_ms * 1e-3),
+                           "status_histogram": np.bincount(stats[:, 3], minlength=5).tolist()},
+                "roofline": roofline,
+                "e2e": {"value": e2e_value, "unit": "problem-iterations/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "steps": e2e_steps, "api": "tfmpc_ilqr_solve_host (pinned host buffers in, host buffers out, synchronous)"},
+                "gpu_launches": int(launches), "clocks": clocks, "step_ms": step_ms}
+        if world == 1 and not args.no_cpu_baseline:
+            sample = args.cpu_sample or {"c3": 65536, "c4": 512, "c5s": 128}[args.workload]
+            v, cores, pi, dt = cpu_baseline(args.workload, T, sample)
+            line["cpu_baseline"] = {"value": v, "unit": "problem-iterations/s", "cores": cores, "kind": "port",
+                                    "sample": f"{sample} problems of the same workload ({pi:.0f} problem-iterations in {dt:.1f} s), "
+                                              "C/OpenMP restatement of the reference algorithm (oracle/), one problem per thread"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="problems per GPU (default: the workload's BASELINE batch)")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="problems in the CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -205,6 +205,10 @@ int tfmpc_lqr_solve_host(int64_t B, int n, int m, int T, const tfmpc_real *F, in
                          int terminal_zero, tfmpc_real *states, tfmpc_real *actions, tfmpc_real *costs, int32_t *status,
                          void *stream);
 
+/* Measurement utility for bench.py: best-of-5 sustained FP32 FMA throughput of the current device in
+ * TFLOP/s (2 flops per FMA) -- the denominator of the CUDA-core roofline.  Synchronous. */
+int tfmpc_measure_fp32_peak(double *tflops, double *kernel_ms);
+
 /* number of kernels this library has launched on behalf of the calling process (monotonic) */
 int64_t tfmpc_kernel_launch_count(void);
 

@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "lib")
 OBJ = os.path.join(HERE, "build")
-SOURCES = ["api.cu", "ilqr_small.cu", "ilqr_warp.cu", "env_ops.cu", "lqr.cu"]
+SOURCES = ["api.cu", "ilqr_small.cu", "ilqr_warp.cu", "env_ops.cu", "lqr.cu", "peak.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

@@ -17,7 +17,7 @@ def make_lqr(state_size, action_size):
     return LQR(F, f, C, c)
 
 
-def make_lqr_linear_navigation(goal, beta):
+def make_lqr_linear_navigation(goal, beta, dtype=None):
     """LQR form of linear navigation: F = [I I], f = 0, C = diag(2,..,2b,..), c = [-2g; 0]
     (envs/__init__.py:21-30).  `goal` may be [n,1] (one problem) or [B,n] / [B,n,1] (a batch that
     shares F, f, C and varies c -- BASELINE config C2).  The reference builds F by tiling I
@@ -34,7 +34,8 @@ def make_lqr_linear_navigation(goal, beta):
     f = np.zeros((n, 1))
     C = np.diag([2.0] * n + [2.0 * float(beta)] * n)
     c = np.concatenate([-2.0 * g, np.zeros_like(g)], axis=1)[..., None]
-    return LQR(F, f, C, c if batched else c[0])
+    kw = {} if dtype is None else {"dtype": dtype}
+    return LQR(F, f, C, c if batched else c[0], **kw)
 
 
 _MODULES = {"navigation": "navigation", "reservoir": "reservoir", "hvac": "hvac", "lqr.navigation": "lqr.navigation",

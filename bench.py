@@ -196,16 +196,25 @@ def run_ours(args):
     x0_h, u0_h = make_inputs(cfg, B, T, seed=1000 + rank)
     x0_pin, u0_pin = torch.from_numpy(x0_h).pin_memory(), torch.from_numpy(u0_h).pin_memory()
     x0, u0 = x0_pin.to(dev), u0_pin.to(dev)
-    out = {"states": torch.empty(B, T + 1, n, device=dev), "actions": torch.empty(B, T, m, device=dev),
-           "costs": torch.empty(B, T + 1, device=dev), "stats": torch.empty(B, 4, dtype=torch.int32, device=dev)}
+    S = max(1, min(args.streams, args.steps))
     nat, opts = env.native(), solver._opts()
-    gathered = [torch.empty(B, device=dev) for _ in range(world)] if world > 1 else None
-    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)   # 256 MB > 126 MB L2
 
-    def step():
-        ops.ilqr_solve(nat, x0, u0, opts, out)
+    def new_out(host=False):
+        kw = {} if host else {"device": dev}
+        o = {"states": torch.empty(B, T + 1, n, **kw), "actions": torch.empty(B, T, m, **kw), "costs": torch.empty(B, T + 1, **kw),
+             "stats": torch.empty(B, 4, dtype=torch.int32, **kw)}
+        return {k: v.pin_memory() for k, v in o.items()} if host else o
+
+    outs = [new_out() for _ in range(S)]
+    gathered = [[torch.empty(B, device=dev) for _ in range(world)] for _ in range(S)] if world > 1 else None
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)   # 256 MB > 126 MB L2
+    streams = [torch.cuda.Stream(device=dev) for _ in range(S)]
+    main = torch.cuda.current_stream()
+
+    def step(slot):
+        ops.ilqr_solve(nat, x0, u0, opts, outs[slot])
         if world > 1:   # the one collective of the sharded solve: per-problem total costs to every rank
-            dist.all_gather(gathered, out["costs"].sum(1))
+            dist.all_gather(gathered[slot], outs[slot]["costs"].sum(1))
 
     def barrier():
         if world > 1:
@@ -213,44 +222,82 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     for _ in range(max(args.warmup, 3)):
-        step()
+        step(0)
+    for i in range(1, S):          # warm every stream's workspace
+        with torch.cuda.stream(streams[i]):
+            step(i)
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
-    launches0 = _native.kernel_launch_count("f32")
+    t_wall0 = time.time()
+
+    # ---- (1) sequential: one batch at a time, L2 flushed between steps -> per-batch latency
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
-    t_wall0 = time.time()
     for s in range(args.steps):
         flush.zero_()                      # evict L2 between timed iterations (not timed)
         ev[s][0].record()
-        step()
+        step(0)
         ev[s][1].record()
     barrier()
-    t_wall1 = time.time()
-    launches = _native.kernel_launch_count("f32") - launches0
-    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
     step_ms = [a.elapsed_time(b) for a, b in ev]
-    total_ms = float(sum(step_ms))
-    stats = out["stats"].cpu().numpy()
+    seq_ms = float(sum(step_ms))
+
+    # ---- (2) pipelined: the same K independent batches issued round-robin on S streams, so the latency-bound tail of
+    #      one batch (few unconverged problems) overlaps the throughput-bound head of the next
+    launches0 = _native.kernel_launch_count("f32")
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(main)
+    for st in streams:
+        st.wait_event(e0)
+    for s in range(args.steps):
+        with torch.cuda.stream(streams[s % S]):
+            step(s % S)
+    for st in streams:
+        done = torch.cuda.Event()
+        done.record(st)
+        main.wait_event(done)
+    e1.record(main)
+    barrier()
+    pipe_ms = float(e0.elapsed_time(e1))
+    launches = _native.kernel_launch_count("f32") - launches0
+    t_wall1 = time.time()
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+
+    stats = outs[0]["stats"].cpu().numpy()
     pi_local = float((stats[:, 0] + 1).sum())
-    t = torch.tensor([total_ms, pi_local], dtype=torch.float64, device=dev)
+    t = torch.tensor([pipe_ms, seq_ms, pi_local], dtype=torch.float64, device=dev)
     if world > 1:
         tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        total_ms, pi_all = float(tmax[0]), float(tsum[1])
+        pipe_ms, seq_ms, pi_all = float(tmax[0]), float(tmax[1]), float(tsum[2])
     else:
         pi_all = pi_local
+    total_ms = pipe_ms if S > 1 else seq_ms
     value = pi_all * args.steps / (total_ms * 1e-3)
 
-    # ---- end to end through the public host-buffer API (pinned inputs -> results on the host), every rank
-    e2e_steps = max(1, min(args.steps, 3))
-    out_h = {"states": torch.empty(B, T + 1, n).pin_memory(), "actions": torch.empty(B, T, m).pin_memory(),
-             "costs": torch.empty(B, T + 1).pin_memory(), "stats": torch.empty(B, 4, dtype=torch.int32).pin_memory()}
-    ops.ilqr_solve_host(nat, x0_pin, u0_pin, opts, out_h)   # warm (allocates the cached device scratch)
+    # ---- end to end through the public host-buffer API: pinned host inputs -> results in host memory, every step.
+    #      S host threads, each with its own env handle and stream (the C ABI is re-entrant across streams).
+    e2e_steps = max(S, min(args.steps, 2 * S))
+    nats = [envs.make_env(cfg).native() for _ in range(S)]
+    houts = [new_out(host=True) for _ in range(S)]
+
+    def e2e_worker(i, count):
+        torch.cuda.set_device(local)
+        with torch.cuda.stream(streams[i]):
+            for _ in range(count):
+                ops.ilqr_solve_host(nats[i], x0_pin, u0_pin, opts, houts[i])
+
+    for i in range(S):
+        e2e_worker(i, 1)                   # warm (allocates each handle's cached device scratch)
     barrier()
+    counts = [e2e_steps // S + (1 if i < e2e_steps % S else 0) for i in range(S)]
+    threads = [threading.Thread(target=e2e_worker, args=(i, counts[i])) for i in range(S)]
     t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        ops.ilqr_solve_host(nat, x0_pin, u0_pin, opts, out_h)
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
     barrier()
     e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
@@ -258,7 +305,7 @@ def run_ours(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = pi_all * e2e_steps / float(te[0])
     h2d = x0_pin.numel() * 4 + u0_pin.numel() * 4
-    d2h = sum(v.numel() * 4 for v in out_h.values())
+    d2h = sum(v.numel() * 4 for v in houts[0].values())
 
     if rank == 0:
         peaks, peak_src = measured_peaks()
@@ -266,17 +313,18 @@ def run_ours(args):
         tf, kms = ctypes.c_double(), ctypes.c_double()
         lib.tfmpc_measure_fp32_peak(ctypes.byref(tf), ctypes.byref(kms))
         flops, byts = algorithmic_work(args.workload, T, stats)
-        kernel_s = total_ms * 1e-3 / args.steps            # one solve kernel per step dominates the step
-        ach_tf, ach_gb = flops / kernel_s / 1e12, byts / kernel_s / 1e9
+        solve_s = total_ms * 1e-3 / args.steps             # device time per solve (launch sequence), pipelined if S > 1
+        ach_tf, ach_gb = flops / solve_s / 1e12, byts / solve_s / 1e9
         fp32 = {"bound": "fp32", "achieved": ach_tf, "peak": tf.value, "unit": "TFLOP/s", "frac": ach_tf / tf.value if tf.value else None,
                 "traffic": None, "peak_source": "FP32 FMA microbenchmark run in this process (tfmpc_measure_fp32_peak); nominal 148 SM x 128 lanes x 2 x clock"}
         hbm = {"bound": "hbm", "achieved": ach_gb, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach_gb / peaks["hbm_gbs"], "traffic": None,
                "peak_source": peak_src}
         primary = fp32 if (fp32["frac"] or 0) >= hbm["frac"] else hbm
         roofline = dict(primary)
-        roofline["kernel"] = "k_solve (thread-per-problem)" if args.workload == "c3" else "kw_solve (lane-per-state)"
-        roofline["algorithmic_flops_per_launch"] = flops
-        roofline["algorithmic_bytes_per_launch"] = byts
+        roofline["kernel"] = ("launch sequence of one solve: k_tick_backward + k_tick_linesearch per tick (thread-per-problem)"
+                              if args.workload == "c3" else "kw_solve (lane-per-state, persistent)")
+        roofline["algorithmic_flops_per_solve"] = flops
+        roofline["algorithmic_bytes_per_solve"] = byts
         roofline["other"] = hbm if primary is fp32 else fp32
         line = {"metric": "batched iLQR problem-iterations/sec", "value": value, "unit": "problem-iterations/s", "n_gpus": world,
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
@@ -284,15 +332,22 @@ def run_ours(args):
                 "config": {"workload": desc, "batch_per_gpu": B, "global_batch": B * world, "horizon": T, "state_dim": n, "action_dim": m,
                            "parallelism": f"batch sharded over {world} GPU(s), no data-path collective"
                                           + ("; one NCCL all-gather of per-problem costs per step" if world > 1 else ""),
+                           "streams": S,
+                           "pipelining": (f"the {args.steps} steps are independent batches issued round-robin on {S} CUDA streams" if S > 1
+                                          else "one batch at a time"),
                            "solver": "reference defaults atol=5e-3 max_iterations=100 mu_min=1e-6 delta_0=2 c1=0 alpha_min=1e-3",
-                           "l2": "256 MB buffer written between timed iterations (L2 flush, untimed); per-step working set 250 MB > 126 MB L2",
+                           "l2": ("pipelined: aggregate working set of the concurrent batches (S x ~420 MB) >> 126 MB L2; "
+                                  "sequential: 256 MB buffer written between timed iterations (untimed L2 flush)"),
                            "mean_iterations_per_solve": float((stats[:, 0] + 1).mean()),
                            "problems_per_s": B * world * args.steps / (total_ms * 1e-3),
                            "status_histogram": np.bincount(stats[:, 3], minlength=5).tolist()},
+                "sequential": {"value": pi_all * args.steps / (seq_ms * 1e-3), "unit": "problem-iterations/s",
+                               "latency_ms_per_batch": seq_ms / args.steps, "step_ms": step_ms},
                 "roofline": roofline,
                 "e2e": {"value": e2e_value, "unit": "problem-iterations/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "steps": e2e_steps, "api": "tfmpc_ilqr_solve_host (pinned host buffers in, host buffers out, synchronous)"},
-                "gpu_launches": int(launches), "clocks": clocks, "step_ms": step_ms}
+                        "steps": e2e_steps, "host_threads": S,
+                        "api": "tfmpc_ilqr_solve_host (pinned host buffers in, host buffers out, synchronous), one call per step"},
+                "gpu_launches": int(launches), "clocks": clocks}
         if world == 1 and not args.no_cpu_baseline:
             sample = args.cpu_sample or {"c3": 65536, "c4": 512, "c5s": 128}[args.workload]
             v, cores, pi, dt = cpu_baseline(args.workload, T, sample)
@@ -315,6 +370,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="problems per GPU (default: the workload's BASELINE batch)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="problems in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--streams", type=int, default=4, help="CUDA streams the independent steps are pipelined over (1 = strictly sequential)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -18,6 +18,10 @@ LIB = os.path.join(HERE, "lib")
 OBJ = os.path.join(HERE, "build")
 SOURCES = ["api.cu", "ilqr_small.cu", "ilqr_warp.cu", "env_ops.cu", "lqr.cu", "peak.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+# fp32 product build: fast intrinsics (MUFU-based division / exp / sqrt, FTZ).  Measured on B200 ("numerics"):
+# 1.5x faster end to end and statistically indistinguishable parity -- same-iteration-count agreement with the fp32 oracle
+# 96.7% with and 96.6% without, against an fp32-vs-fp64 noise band of 96.1%.  The fp64 verification build stays IEEE.
+F32_FLAGS = "--use_fast_math"
 COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 
 
@@ -59,7 +63,7 @@ def build(force=False, verbose=False, precisions=("f32", "f64")):
         outputs[prec] = out
         if not force and os.path.exists(out) and os.path.getmtime(out) >= newest:
             continue
-        extra = ["-DTFMPC_F64"] if prec == "f64" else []
+        extra = ["-DTFMPC_F64"] if prec == "f64" else ([f for f in os.environ.get("TFMPC_F32_FLAGS", F32_FLAGS).split() if f])
         for s in SOURCES:
             jobs.append((os.path.join(CSRC, s), os.path.join(OBJ, f"{os.path.splitext(s)[0]}_{prec}.o"), extra, verbose))
     if jobs:

@@ -6,6 +6,8 @@
 // "hard parts").  Data layout: the per-problem trajectories live in a struct-of-arrays
 // workspace ws[row][slot] with the problem slot fastest, so the 32 lanes of a warp read and
 // write 32 consecutive words (one 128-byte line) for every row they touch.
+#include <algorithm>
+
 #include "small_core.cuh"
 
 namespace {
@@ -56,53 +58,227 @@ __global__ void __launch_bounds__(kThreads) k_forward(EnvSmall e, int64_t B, int
   J[b] = Jb; residual[b] = res;
 }
 
-// rows of the struct-of-arrays workspace, per problem slot
-template <int N, int M>
-__host__ __device__ constexpr int64_t ws_rows(int T) {
-  return 2 * ((int64_t)(T + 1) * N + (int64_t)T * M) + (int64_t)T * M * N + (int64_t)T * M;
+// ------------------------------------------------------------------ the batched solve, as per-tick kernels
+// iLQR.solve for B problems = a fixed launch sequence with no host round trip:
+//     k_init, then per tick { k_tick_backward, k_tick_linesearch }, then k_costs + 3 x k_transpose_out.
+// A tick is one turn of the reference's inner loop (ilqr.py:238-270) for every still-active problem.
+//  * k_tick_backward   one thread per ACTIVE problem (compacted index list): linearise + Riccati sweep + g_norm test.
+//  * k_tick_linesearch GA (= 4) lanes per active problem: the lanes roll out GA consecutive line-search
+//                      step sizes concurrently, each into its own candidate buffer; the FIRST accepted alpha
+//                      (lowest index, ilqr.py:322-353) is found with a warp ballot; further passes of GA
+//                      alphas run only for the groups that rejected all of them.  The group leader then
+//                      applies the mu/delta schedule and convergence tests (tick_finish) and re-appends the
+//                      problem to the next tick's active list (warp-aggregated atomic).
+// Accepting a candidate is a buffer-index switch (p.cur), not a copy: each problem owns 1 + GA
+// trajectory buffers.  Converged problems drop out of the list, so late ticks touch few problems and
+// cost only their launch latency.
+constexpr int GA = 4;            // line-search lanes (and candidate buffers) per problem
+constexpr int NBUF = 1 + GA;
+constexpr int kExtraTicks = 24;  // ticks beyond max_iterations available to regularisation retries (ilqr.py:267-270)
+
+struct WS {  // carve-up of the workspace (all arrays struct-of-arrays, slot fastest)
+  int *count;                    // [2] active counts (ping-pong)
+  int *list[2];                  // [S] active problem slots
+  int *iteration, *n_bwd, *n_fwd, *status, *cur, *phase, *guard;
+  double *mu, *delta;
+  real *J_hat, *dV1, *dV2;
+  real *traj;                    // NBUF x (nx + nu) rows
+  real *K, *k, *cost;            // nu*N, nu, T+1 rows
+  int64_t S;
+};
+
+__host__ __device__ inline int64_t ws_bytes_for(int64_t S, int T, int N, int M) {
+  int64_t nx = (int64_t)(T + 1) * N, nu = (int64_t)T * M;
+  int64_t rows = NBUF * (nx + nu) + nu * N + nu + (T + 1);
+  return 256 + S * (2 * 4 + 7 * 4 + 2 * 8 + 3 * (int64_t)sizeof(real)) + rows * S * (int64_t)sizeof(real) + 64;
 }
 
-// The whole iLQR.solve for one problem per thread: start rollout, then the outer loop with the
-// mu/delta schedule, convergence tests and line search all on the device (no host round trip).
+inline WS carve(void *ws, int64_t S, int T, int N, int M) {
+  WS w;
+  char *p = (char *)ws;
+  w.S = S;
+  w.count = (int *)p; p += 256;
+  w.mu = (double *)p; p += S * 8;
+  w.delta = (double *)p; p += S * 8;
+  w.list[0] = (int *)p; p += S * 4;
+  w.list[1] = (int *)p; p += S * 4;
+  int **ints[7] = {&w.iteration, &w.n_bwd, &w.n_fwd, &w.status, &w.cur, &w.phase, &w.guard};
+  for (int i = 0; i < 7; i++) { *ints[i] = (int *)p; p += S * 4; }
+  real **reals[3] = {&w.J_hat, &w.dV1, &w.dV2};
+  for (int i = 0; i < 3; i++) { *reals[i] = (real *)p; p += S * sizeof(real); }
+  p = (char *)(((uintptr_t)p + 15) & ~(uintptr_t)15);
+  int64_t nx = (int64_t)(T + 1) * N, nu = (int64_t)T * M;
+  w.traj = (real *)p; p += NBUF * (nx + nu) * S * sizeof(real);
+  w.K = (real *)p; p += nu * N * S * sizeof(real);
+  w.k = (real *)p; p += nu * S * sizeof(real);
+  w.cost = (real *)p;
+  return w;
+}
+
+template <int N, int M>
+__device__ __forceinline__ View bufX(const WS &w, int T, int buf, int64_t b) {
+  return View{w.traj + (int64_t)buf * ((int64_t)(T + 1) * N + (int64_t)T * M) * w.S + b, w.S};
+}
+template <int N, int M>
+__device__ __forceinline__ View bufU(const WS &w, int T, int buf, int64_t b) {
+  return View{w.traj + ((int64_t)buf * ((int64_t)(T + 1) * N + (int64_t)T * M) + (int64_t)(T + 1) * N) * w.S + b, w.S};
+}
+
+__device__ __forceinline__ void load_prob(const WS &w, int64_t b, Prob &p) {
+  p.mu = w.mu[b]; p.delta = w.delta[b]; p.iteration = w.iteration[b]; p.n_bwd = w.n_bwd[b]; p.n_fwd = w.n_fwd[b];
+  p.status = w.status[b]; p.cur = w.cur[b]; p.phase = w.phase[b]; p.guard = w.guard[b];
+  p.J_hat = w.J_hat[b]; p.dV1 = w.dV1[b]; p.dV2 = w.dV2[b];
+}
+
 template <int KIND, int N, int M>
-__global__ void __launch_bounds__(kThreads) k_solve(EnvSmall e, IlqrOpts o, int64_t B, int64_t S, int T,
-                                                    const real *__restrict__ x0, const real *__restrict__ u_init,
-                                                    real *__restrict__ ws, real *__restrict__ states, real *__restrict__ actions,
-                                                    real *__restrict__ costs, int32_t *__restrict__ stats) {
+__global__ void __launch_bounds__(kThreads) k_init(EnvSmall e, int64_t B, int T, const real *__restrict__ x0,
+                                                   const real *__restrict__ u_init, WS w) {
+  int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b == 0) { w.count[0] = (int)B; w.count[1] = 0; }
+  if (b >= B) return;
+  Prob p;
+  prob_init(p);
+  w.mu[b] = p.mu; w.delta[b] = p.delta; w.iteration[b] = 0; w.n_bwd[b] = 0; w.n_fwd[b] = 0; w.status[b] = p.status;
+  w.cur[b] = 0; w.phase[b] = PH_SEARCH; w.guard[b] = 0;
+  w.list[0][b] = (int)b;
+  real x[N];
+#pragma unroll
+  for (int i = 0; i < N; i++) x[i] = x0[b * N + i];
+  CView Ui = {u_init + b * T * M, 1};
+  const View none = {nullptr, 0};
+  start_pass<KIND, N, M>(e, T, x, Ui, bufX<N, M>(w, T, 0, b), bufU<N, M>(w, T, 0, b), none);
+}
+
+template <int KIND, int N, int M>
+__global__ void __launch_bounds__(kThreads) k_tick_backward(EnvSmall e, IlqrOpts o, int T, WS w, int parity) {
+  const int cnt = w.count[parity];
+  if (blockIdx.x == 0 && threadIdx.x == 0) w.count[parity ^ 1] = 0;  // filled by this tick's line-search kernel
+  const int *__restrict__ list = w.list[parity];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
+    const int64_t b = list[i];
+    Prob p;
+    load_prob(w, b, p);
+    View Kv = {w.K + b, w.S}, kv = {w.k + b, w.S};
+    tick_backward<KIND, N, M>(e, o, T, bufX<N, M>(w, T, p.cur, b), bufU<N, M>(w, T, p.cur, b), Kv, kv, p);
+    w.n_bwd[b] = p.n_bwd; w.status[b] = p.status; w.phase[b] = p.phase;
+    w.J_hat[b] = p.J_hat; w.dV1[b] = p.dV1; w.dV2[b] = p.dV2;
+  }
+}
+
+template <int KIND, int N, int M>
+__global__ void __launch_bounds__(kThreads) k_tick_linesearch(EnvSmall e, IlqrOpts o, int T, WS w, int parity) {
+  constexpr unsigned FULL = 0xffffffffu;
+  constexpr int PASSES = (N_ALPHA + GA - 1) / GA;
+  const int cnt = w.count[parity];
+  const int *__restrict__ list = w.list[parity];
+  int *__restrict__ next = w.list[parity ^ 1];
+  const int lane = threadIdx.x & 31, la = lane % GA, sub = lane / GA;
+  const int groups_per_warp = 32 / GA;
+  const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  const View none = {nullptr, 0};
+  for (int base = warp_global * groups_per_warp; base < cnt; base += nwarps * groups_per_warp) {  // warp-uniform trip count
+    const int gi = base + sub;
+    const bool valid = gi < cnt;
+    const int64_t b = valid ? list[gi] : list[0];
+    Prob p;
+    load_prob(w, b, p);
+    const bool was_search = valid && p.phase == PH_SEARCH;
+    bool searching = was_search, accept = false;
+    real residual = 0;
+    int rollouts = 0, cand = 0;
+    View Kv = {w.K + b, w.S}, kv = {w.k + b, w.S};
+    const View Xh = bufX<N, M>(w, T, p.cur, b), Uh = bufU<N, M>(w, T, p.cur, b);
+    const int mybuf = la + (la >= p.cur ? 1 : 0);  // this lane's candidate buffer: the la-th buffer that is not the nominal
+    for (int pass = 0; pass < PASSES; pass++) {
+      if (!__any_sync(FULL, searching)) break;
+      const int ai = pass * GA + la;
+      const bool run = searching && ai < N_ALPHA;
+      real J = 0, res = 0;
+      bool acc = false;
+      if (run) {
+        const real alpha = o.alphas[ai];
+        forward_pass<KIND, N, M>(e, T, Xh, Uh, Kv, kv, alpha, bufX<N, M>(w, T, mybuf, b), bufU<N, M>(w, T, mybuf, b), none, J, res);
+        acc = ls_accepts(o, alpha, p.J_hat, p.dV1, p.dV2, J);
+      }
+      const unsigned gm = (__ballot_sync(FULL, acc) >> (sub * GA)) & ((1u << GA) - 1u);
+      const int last = min(GA - 1, N_ALPHA - 1 - pass * GA);      // last alpha lane of this pass
+      const int src = gm ? (__ffs(gm) - 1) : last;                 // first accepted lane, else the last candidate
+      const real r_src = __shfl_sync(FULL, res, src, GA);
+      if (searching) {
+        residual = r_src;
+        cand = src + (src >= p.cur ? 1 : 0);
+        if (gm) { accept = true; rollouts = pass * GA + src + 1; searching = false; }
+        else { rollouts = pass * GA + last + 1; if (pass == PASSES - 1) searching = false; }
+      }
+    }
+    bool keep = false;
+    if (valid && la == 0) {
+      if (was_search) {
+        if (tick_finish(o, accept, residual, rollouts, p)) p.cur = cand;
+        w.mu[b] = p.mu; w.delta[b] = p.delta; w.iteration[b] = p.iteration; w.n_fwd[b] = p.n_fwd; w.status[b] = p.status;
+        w.cur[b] = p.cur; w.phase[b] = p.phase; w.guard[b] = p.guard;
+      }
+      keep = p.phase != PH_DONE;
+    }
+    // warp-aggregated append to the next tick's active list (keeps slot order within a warp)
+    const unsigned km = __ballot_sync(FULL, keep);
+    if (km) {
+      int pos = 0;
+      if (lane == __ffs(km) - 1) pos = atomicAdd(&w.count[parity ^ 1], __popc(km));
+      pos = __shfl_sync(FULL, pos, __ffs(km) - 1);
+      if (keep) next[pos + __popc(km & ((1u << lane) - 1u))] = (int)b;
+    }
+  }
+}
+
+// cost(x_t, u_t) of the final nominal (what the accepting forward pass / start computed, ilqr.py:199,208) + stats
+template <int KIND, int N, int M>
+__global__ void __launch_bounds__(kThreads) k_costs(EnvSmall e, int64_t B, int T, WS w, int32_t *__restrict__ stats) {
   int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
-  const int64_t nx = (int64_t)(T + 1) * N, nu = (int64_t)T * M;
-  real *base = ws + b;
-  View X[2] = {{base, S}, {base + (nx + nu) * S, S}};
-  View U[2] = {{base + nx * S, S}, {base + (2 * nx + nu) * S, S}};
-  View Kv = {base + 2 * (nx + nu) * S, S};
-  View kv = {base + (2 * (nx + nu) + nu * N) * S, S};
-  const View none = {nullptr, 0};
-  {
-    real x[N];
-#pragma unroll
-    for (int i = 0; i < N; i++) x[i] = x0[b * N + i];
-    CView Ui = {u_init + b * nu, 1};
-    start_pass<KIND, N, M>(e, T, x, Ui, X[0], U[0], none);
-  }
-  int32_t st[4];
-  int cur = solve_one<KIND, N, M>(e, o, T, X, U, Kv, kv, st);
-  // emit the converged nominal in the reference's layouts; costs are cost(x_t, u_t) of that
-  // nominal, i.e. exactly what the accepting forward pass (or start) computed (ilqr.py:199,208)
-  real *so = states + b * nx, *ao = actions + b * nu, *co = costs + b * (T + 1);
+  const int cur = w.cur[b];
+  const View X = bufX<N, M>(w, T, cur, b), U = bufU<N, M>(w, T, cur, b);
   real x[N], u[M];
   for (int t = 0; t < T; t++) {
 #pragma unroll
-    for (int i = 0; i < N; i++) { x[i] = X[cur](t * N + i); so[t * N + i] = x[i]; }
+    for (int i = 0; i < N; i++) x[i] = X(t * N + i);
 #pragma unroll
-    for (int i = 0; i < M; i++) { u[i] = U[cur](t * M + i); ao[t * M + i] = u[i]; }
-    co[t] = env_cost<KIND, N, M>(e, x, u);
+    for (int i = 0; i < M; i++) u[i] = U(t * M + i);
+    w.cost[(int64_t)t * w.S + b] = env_cost<KIND, N, M>(e, x, u);
   }
 #pragma unroll
-  for (int i = 0; i < N; i++) { x[i] = X[cur](T * N + i); so[T * N + i] = x[i]; }
-  co[T] = env_final_cost<KIND, N, M>(e, x);
-#pragma unroll
-  for (int i = 0; i < 4; i++) stats[b * 4 + i] = st[i];
+  for (int i = 0; i < N; i++) x[i] = X(T * N + i);
+  w.cost[(int64_t)T * w.S + b] = env_final_cost<KIND, N, M>(e, x);
+  int st = w.status[b];
+  if (w.phase[b] != PH_DONE) st = TFMPC_ST_REGLOOP;  // ran out of ticks (more than kExtraTicks rejected line searches)
+  reinterpret_cast<int4 *>(stats)[b] = make_int4(w.iteration[b], w.n_bwd[b], w.n_fwd[b], st);
+}
+
+// out[b][r] = src_b[r * S + b]: 32 x 32 tiles through shared memory so that both the struct-of-arrays reads and
+// the reference-layout writes are coalesced.  which: 0 = states, 1 = actions (buffer chosen per problem by cur), 2 = costs.
+template <int N, int M>
+__global__ void __launch_bounds__(128) k_transpose_out(int64_t B, int T, WS w, int which, int nrows, real *__restrict__ out) {
+  __shared__ real tile[4][32][33];
+  const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
+  const int64_t slot0 = ((int64_t)blockIdx.x * 4 + wq) * 32;
+  if (slot0 >= B) return;
+  const int64_t b = slot0 + lane;
+  const bool vb = b < B;
+  const real *src = w.cost + (vb ? b : 0);
+  if (which < 2 && vb) {
+    const int cur = w.cur[b];
+    src = (which == 0 ? bufX<N, M>(w, T, cur, b) : bufU<N, M>(w, T, cur, b)).p;
+  }
+  for (int r0 = 0; r0 < nrows; r0 += 32) {
+#pragma unroll 4
+    for (int rr = 0; rr < 32; rr++)
+      if (vb && r0 + rr < nrows) tile[wq][rr][lane] = src[(int64_t)(r0 + rr) * w.S];
+    __syncwarp();
+#pragma unroll 4
+    for (int ss = 0; ss < 32; ss++)
+      if (slot0 + ss < B && r0 + lane < nrows) out[(slot0 + ss) * nrows + r0 + lane] = tile[wq][lane][ss];
+    __syncwarp();
+  }
 }
 
 template <int M>
@@ -180,17 +356,46 @@ int small_ilqr_forward(const tfmpc_env *e, int64_t B, int T, const real *states,
 
 static int64_t padded_slots(int64_t B) { return (B + 31) / 32 * 32; }
 
-int64_t small_ilqr_workspace_bytes(const tfmpc_env *e, int64_t B, int T) {
-  int64_t N = e->n, M = e->m;
-  int64_t rows = 2 * ((int64_t)(T + 1) * N + (int64_t)T * M) + (int64_t)T * M * N + (int64_t)T * M;
-  return rows * padded_slots(B) * (int64_t)sizeof(real);
+int64_t small_ilqr_workspace_bytes(const tfmpc_env *e, int64_t B, int T) { return ws_bytes_for(padded_slots(B), T, e->n, e->m); }
+
+static int device_sms(int device) {
+  static int cached[64] = {0};
+  if (device >= 0 && device < 64 && cached[device]) return cached[device];
+  int v = 148;
+  cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device);
+  if (device >= 0 && device < 64) cached[device] = v;
+  return v;
+}
+
+template <int KIND, int N, int M>
+static int solve_launch(const tfmpc_env *e, int64_t B, int T, const real *x0, const real *u_init, const IlqrOpts &o, real *states,
+                        real *actions, real *costs, int32_t *stats, void *ws, cudaStream_t s) {
+  const WS w = carve(ws, padded_slots(B), T, N, M);
+  const int sms = device_sms(e->device);
+  const unsigned gB = grid_for(B);
+  k_init<KIND, N, M><<<gB, kThreads, 0, s>>>(e->es, B, T, x0, u_init, w);
+  // persistent-style grids: enough threads for every active problem (x GA lanes), capped at a few waves
+  const unsigned g_bwd = (unsigned)std::min<int64_t>(gB, (int64_t)sms * 16);
+  const unsigned g_ls = (unsigned)std::min<int64_t>((B * GA + kThreads - 1) / kThreads, (int64_t)sms * 16);
+  const int ticks = o.max_iterations + kExtraTicks;
+  for (int t = 0; t < ticks; t++) {
+    k_tick_backward<KIND, N, M><<<g_bwd, kThreads, 0, s>>>(e->es, o, T, w, t & 1);
+    k_tick_linesearch<KIND, N, M><<<g_ls, kThreads, 0, s>>>(e->es, o, T, w, t & 1);
+  }
+  k_costs<KIND, N, M><<<gB, kThreads, 0, s>>>(e->es, B, T, w, stats);
+  const unsigned gT = (unsigned)((B + 127) / 128);
+  k_transpose_out<N, M><<<gT, 128, 0, s>>>(B, T, w, 0, (T + 1) * N, states);
+  k_transpose_out<N, M><<<gT, 128, 0, s>>>(B, T, w, 1, T * M, actions);
+  k_transpose_out<N, M><<<gT, 128, 0, s>>>(B, T, w, 2, T + 1, costs);
+  tfmpc_count_launch(2 * ticks + 4);
+  return TFMPC_OK;
 }
 
 int small_ilqr_solve(const tfmpc_env *e, int64_t B, int T, const real *x0, const real *u_init, const IlqrOpts &o, real *states,
                      real *actions, real *costs, int32_t *stats, void *ws, int64_t ws_bytes, cudaStream_t s) {
   if (ws_bytes < small_ilqr_workspace_bytes(e, B, T)) return tfmpc_set_error(TFMPC_E_WORKSPACE, "workspace too small");
-  int64_t S = padded_slots(B);
-#define CALL(KD, N, M) k_solve<KD, N, M><<<grid_for(B), kThreads, 0, s>>>(e->es, o, B, S, T, x0, u_init, (real *)ws, states, actions, costs, stats)
+  if (B > 0x7fffffff) return tfmpc_set_error(TFMPC_E_INVALID, "batch too large");
+#define CALL(KD, N, M) { int rc_ = solve_launch<KD, N, M>(e, B, T, x0, u_init, o, states, actions, costs, stats, ws, s); if (rc_) return rc_; }
   SMALL_DISPATCH(e, CALL);
 #undef CALL
   LAUNCH_CHECK();

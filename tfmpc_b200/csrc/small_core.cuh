@@ -240,8 +240,17 @@ HD int boxqp(const real *H, const real *q, const real *lo, const real *hi, real 
     real vc;
     for (;;) {  // :82-95
       real st = (real)step;
+      bool moved = false;
 #pragma unroll
-      for (int i = 0; i < M; i++) xc[i] = r_clip(x[i] + st * search[i], lo[i], hi[i]);
+      for (int i = 0; i < M; i++) { xc[i] = r_clip(x[i] + st * search[i], lo[i], hi[i]); moved = moved || (xc[i] != x[i]); }
+      if (!moved) {
+        // Degenerate backtracking, fast-forwarded.  The candidate equals x bit for bit, so f(xc) == old_value
+        // exactly, the Armijo ratio is -0 < 0.1, and every further halving of the step reproduces the same xc:
+        // the reference spins here until step < 1e-22 (100 evaluations) and leaves with x and value unchanged.
+        // About 2% of the box-QPs of the navigation workload end this way ("box-QP").
+        vc = old_value;
+        break;
+      }
       vc = qp_value<M>(H, q, xc);
       if (!((vc - old_value) / (st * sdotg) < armijo)) break;
       step *= 0.6;
@@ -261,11 +270,22 @@ HD int boxqp(const real *H, const real *q, const real *lo, const real *hi, real 
 }
 
 // ------------------------------------------------------------------ iLQR backward, one timestep
+// Structural zeros of the analytic linearisation, known at compile time per environment.  Skipping a
+// product with a structural zero (or the addition of one) is exact, so the result equals the dense
+// product the reference forms -- only the instruction count changes.
+template <int KIND>
+struct Traits {
+  static constexpr bool fu_diag = true;                       // f_u = I (NavigationLQR) or lambda I (Navigation)
+  static constexpr bool fx_diag = (KIND == TFMPC_ENV_NAVLQR);  // f_x = I
+  static constexpr bool lxx_diag = true, luu_diag = true, lxu_zero = true;
+};
+
 // tfmpc/solvers/ilqr.py:108-170 with the controllers of :357-387.  V_x, V_xx, J, dV1, dV2 are
 // carried across timesteps.  Returns 0, 1 (unconstrained Cholesky failed) or 2 (box-QP failed).
 template <int KIND, int N, int M>
 HD int backward_step(const EnvSmall &e, const Lin<N, M> &L, const real *u, real mu, real *V_x, real *V_xx, real &J, real &dV1,
                      real &dV2, real *K, real *k) {
+  typedef Traits<KIND> TR;
   real Q_x[N], Q_u[M], Q_xx[N * N], Q_uu[M * M], Q_ux[M * N], Q_uu_reg[M * M], Q_ux_reg[M * N];
   real fxTV[N * N], fuTV[M * N], fuTVr[M * N];
   int status = 0;
@@ -273,14 +293,20 @@ HD int backward_step(const EnvSmall &e, const Lin<N, M> &L, const real *u, real 
   for (int i = 0; i < N; i++) {  // :122
     real s = 0;
 #pragma unroll
-    for (int p = 0; p < N; p++) s += L.f_x[p * N + i] * V_x[p];
+    for (int p = 0; p < N; p++) {
+      if (TR::fx_diag && p != i) continue;
+      s += L.f_x[p * N + i] * V_x[p];
+    }
     Q_x[i] = L.l_x[i] + s;
   }
 #pragma unroll
   for (int i = 0; i < M; i++) {  // :123
     real s = 0;
 #pragma unroll
-    for (int p = 0; p < N; p++) s += L.f_u[p * M + i] * V_x[p];
+    for (int p = 0; p < N; p++) {
+      if (TR::fu_diag && p != i) continue;
+      s += L.f_u[p * M + i] * V_x[p];
+    }
     Q_u[i] = L.l_u[i] + s;
   }
 #pragma unroll
@@ -289,7 +315,10 @@ HD int backward_step(const EnvSmall &e, const Lin<N, M> &L, const real *u, real 
     for (int j = 0; j < N; j++) {  // :125
       real s = 0;
 #pragma unroll
-      for (int p = 0; p < N; p++) s += L.f_x[p * N + i] * V_xx[p * N + j];
+      for (int p = 0; p < N; p++) {
+        if (TR::fx_diag && p != i) continue;
+        s += L.f_x[p * N + i] * V_xx[p * N + j];
+      }
       fxTV[i * N + j] = s;
     }
 #pragma unroll
@@ -299,6 +328,7 @@ HD int backward_step(const EnvSmall &e, const Lin<N, M> &L, const real *u, real 
       real s = 0, sr = 0;
 #pragma unroll
       for (int p = 0; p < N; p++) {
+        if (TR::fu_diag && p != i) continue;
         s += L.f_u[p * M + i] * V_xx[p * N + j];
         sr += L.f_u[p * M + i] * (p == j ? V_xx[p * N + j] + mu * (real)1 : V_xx[p * N + j]);
       }
@@ -311,8 +341,11 @@ HD int backward_step(const EnvSmall &e, const Lin<N, M> &L, const real *u, real 
     for (int j = 0; j < N; j++) {  // :129
       real s = 0;
 #pragma unroll
-      for (int p = 0; p < N; p++) s += fxTV[i * N + p] * L.f_x[p * N + j];
-      Q_xx[i * N + j] = L.l_xx[i * N + j] + s;
+      for (int p = 0; p < N; p++) {
+        if (TR::fx_diag && p != j) continue;
+        s += fxTV[i * N + p] * L.f_x[p * N + j];
+      }
+      Q_xx[i * N + j] = (TR::lxx_diag && i != j) ? s : L.l_xx[i * N + j] + s;
     }
 #pragma unroll
   for (int i = 0; i < M; i++) {
@@ -320,17 +353,25 @@ HD int backward_step(const EnvSmall &e, const Lin<N, M> &L, const real *u, real 
     for (int j = 0; j < M; j++) {  // :130, :133
       real s = 0, sr = 0;
 #pragma unroll
-      for (int p = 0; p < N; p++) { s += fuTV[i * N + p] * L.f_u[p * M + j]; sr += fuTVr[i * N + p] * L.f_u[p * M + j]; }
-      Q_uu[i * M + j] = L.l_uu[i * M + j] + s;
-      Q_uu_reg[i * M + j] = L.l_uu[i * M + j] + sr;
+      for (int p = 0; p < N; p++) {
+        if (TR::fu_diag && p != j) continue;
+        s += fuTV[i * N + p] * L.f_u[p * M + j];
+        sr += fuTVr[i * N + p] * L.f_u[p * M + j];
+      }
+      Q_uu[i * M + j] = (TR::luu_diag && i != j) ? s : L.l_uu[i * M + j] + s;
+      Q_uu_reg[i * M + j] = (TR::luu_diag && i != j) ? sr : L.l_uu[i * M + j] + sr;
     }
 #pragma unroll
     for (int j = 0; j < N; j++) {  // :131, :134 (l_xu^T)
       real s = 0, sr = 0;
 #pragma unroll
-      for (int p = 0; p < N; p++) { s += fuTV[i * N + p] * L.f_x[p * N + j]; sr += fuTVr[i * N + p] * L.f_x[p * N + j]; }
-      Q_ux[i * N + j] = L.l_xu[j * M + i] + s;
-      Q_ux_reg[i * N + j] = L.l_xu[j * M + i] + sr;
+      for (int p = 0; p < N; p++) {
+        if (TR::fx_diag && p != j) continue;
+        s += fuTV[i * N + p] * L.f_x[p * N + j];
+        sr += fuTVr[i * N + p] * L.f_x[p * N + j];
+      }
+      Q_ux[i * N + j] = TR::lxu_zero ? s : L.l_xu[j * M + i] + s;
+      Q_ux_reg[i * N + j] = TR::lxu_zero ? sr : L.l_xu[j * M + i] + sr;
     }
   }
   if (e.bounded) {  // :136
@@ -489,30 +530,50 @@ HD int backward_pass(const EnvSmall &e, int T, const XV &X, const UV &U, real mu
 }
 
 // iLQR.forward (ilqr.py:174-212).  cs may be a null view (p == nullptr) when costs are not wanted.
+// The nominal operands of step t+1 are loaded while step t computes (explicit software prefetch): in the
+// line search this loop is bound by memory latency otherwise.
 template <int KIND, int N, int M, class XV, class UV, class KV>
 HD void forward_pass(const EnvSmall &e, int T, const XV &Xh, const UV &Uh, const KV &Kv, const KV &kv, real alpha, const View &Xo,
                      const View &Uo, const View &Co, real &J, real &residual) {
   real x[N], u[M], xn[N];
+  real xh[N], uh[M], Kt[M * N], kt[M];
   J = 0; residual = 0;
 #pragma unroll
-  for (int i = 0; i < N; i++) { x[i] = Xh(i); Xo(i) = x[i]; }
+  for (int i = 0; i < N; i++) { xh[i] = Xh(i); x[i] = xh[i]; Xo(i) = x[i]; }
+#pragma unroll
+  for (int i = 0; i < M; i++) { uh[i] = Uh(i); kt[i] = kv(i); }
+#pragma unroll
+  for (int i = 0; i < M * N; i++) Kt[i] = Kv(i);
   for (int t = 0; t < T; t++) {
+    real xh_n[N], uh_n[M], K_n[M * N], k_n[M];
+    const int tn = (t + 1 < T) ? t + 1 : t;  // last step re-reads itself (harmless) instead of branching
+#pragma unroll
+    for (int i = 0; i < N; i++) xh_n[i] = Xh(tn * N + i);
+#pragma unroll
+    for (int i = 0; i < M; i++) { uh_n[i] = Uh(tn * M + i); k_n[i] = kv(tn * M + i); }
+#pragma unroll
+    for (int i = 0; i < M * N; i++) K_n[i] = Kv(tn * M * N + i);
 #pragma unroll
     for (int i = 0; i < M; i++) {
       real s = 0;
 #pragma unroll
-      for (int j = 0; j < N; j++) s += Kv(t * M * N + i * N + j) * (x[j] - Xh(t * N + j));
-      real du = alpha * kv(t * M + i) + s;            // :194
-      u[i] = r_clip(Uh(t * M + i) + du, e.low[i], e.high[i]);  // :196-197
-      residual = r_max(residual, r_abs(du));          // :206 (pre-clip)
-      Uo(t * M + i) = u[i];
+      for (int j = 0; j < N; j++) s += Kt[i * N + j] * (x[j] - xh[j]);
+      real du = alpha * kt[i] + s;                            // :194
+      u[i] = r_clip(uh[i] + du, e.low[i], e.high[i]);         // :196-197
+      residual = r_max(residual, r_abs(du));                  // :206 (pre-clip)
     }
     real c = env_cost<KIND, N, M>(e, x, u);
     env_step<KIND, N, M>(e, x, u, xn);
+#pragma unroll
+    for (int i = 0; i < M; i++) Uo(t * M + i) = u[i];
     if (Co.p) Co(t) = c;
     J += c;
 #pragma unroll
-    for (int i = 0; i < N; i++) { x[i] = xn[i]; Xo((t + 1) * N + i) = x[i]; }
+    for (int i = 0; i < N; i++) { x[i] = xn[i]; Xo((t + 1) * N + i) = x[i]; xh[i] = xh_n[i]; }
+#pragma unroll
+    for (int i = 0; i < M; i++) { uh[i] = uh_n[i]; kt[i] = k_n[i]; }
+#pragma unroll
+    for (int i = 0; i < M * N; i++) Kt[i] = K_n[i];
   }
   real cf = env_final_cost<KIND, N, M>(e, x);
   if (Co.p) Co(T) = cf;
@@ -536,62 +597,97 @@ HD void start_pass(const EnvSmall &e, int T, const real *x0, const UV &Ui, const
   if (Co.p) Co(T) = env_final_cost<KIND, N, M>(e, x);
 }
 
-// ------------------------------------------------------------------ whole solve, one problem
-// iLQR.solve (ilqr.py:214-283) + _backward (:285-315) + _forward (:317-355).  The nominal and
-// candidate trajectories ping-pong between two (X, U) buffer pairs; `cur` is the pair holding
-// the nominal at exit.  stats = {iteration index, backward passes, rollouts, status}.
+// ------------------------------------------------------------------ the solve, as per-problem TICKS
+// iLQR.solve (ilqr.py:214-283) + _backward (:285-315) + _forward (:317-355) cut into the pieces the
+// kernels run once per "tick": one backward pass, one line search, one schedule update.  A tick is one
+// turn of the reference's inner `while True` (:238); the outer iteration index advances only when a
+// step is accepted, exactly as in the reference.  The same functions are composed sequentially by
+// solve_one() below (used by the host-emulation harness) and in parallel by the kernels.
+enum { PH_SEARCH = 0, PH_DONE = 1 };
+
+struct Prob {            // per-problem solver state
+  double mu, delta;      // python floats in the reference (ilqr.py:215-216)
+  int iteration, n_bwd, n_fwd, status, cur, phase, guard;
+  real J_hat, dV1, dV2;
+};
+
+HD void prob_init(Prob &p) {
+  p.mu = 0.0; p.delta = 1.0; p.iteration = 0; p.n_bwd = 0; p.n_fwd = 0; p.status = TFMPC_ST_MAXITER; p.cur = 0; p.phase = PH_SEARCH;
+  p.guard = 0; p.J_hat = 0; p.dV1 = 0; p.dV2 = 0;
+}
+
+// _backward (:285-315) + the g_norm test (:243-248).  Leaves p.phase = PH_SEARCH if a line search must follow.
+template <int KIND, int N, int M>
+HD void tick_backward(const EnvSmall &e, const IlqrOpts &o, int T, const View &X, const View &U, const View &Kv, const View &kv, Prob &p) {
+  real gsum;
+  double mu_l = p.mu, delta_l = p.delta;  // the retry bump is local, ilqr.py:308-309,315
+  int bst, tries = 0;
+  for (;;) {
+    bst = backward_pass<KIND, N, M>(e, T, X, U, (real)mu_l, Kv, kv, p.J_hat, p.dV1, p.dV2, gsum);
+    p.n_bwd++;
+    if (bst != 1 || ++tries > 200) break;
+    delta_l = fmax(o.delta_0, delta_l * o.delta_0);
+    mu_l = fmax(o.mu_min, mu_l * delta_l);
+  }
+  p.phase = PH_SEARCH;
+  if (bst) { p.status = TFMPC_ST_NONPD; p.phase = PH_DONE; return; }
+  real g = gsum / (real)T;  // :243
+  if (!(g == g)) { p.status = TFMPC_ST_NAN; p.phase = PH_DONE; return; }
+  if (g < o.atol) { p.status = TFMPC_ST_CONVERGED; p.phase = PH_DONE; }  // :245-248 (nominal kept)
+}
+
+// acceptance test of one candidate, _forward :339-351
+HD bool ls_accepts(const IlqrOpts &o, real alpha, real J_hat, real dV1, real dV2, real J) {
+  real delta_J = -alpha * (dV1 + alpha * dV2);
+  real dcost = J_hat - J;
+  real z = (delta_J > 0) ? dcost / delta_J : r_sgn(dcost);
+  return z >= o.c1;
+}
+
+// What solve() does with the outcome of the line search (:253-270).  `rollouts` = candidates the
+// reference would have evaluated; `residual` belongs to the last of them.  Returns true when that last
+// candidate becomes the nominal.
+HD bool tick_finish(const IlqrOpts &o, bool accept, real residual, int rollouts, Prob &p) {
+  p.n_fwd += rollouts;
+  if (residual < o.atol) {  // :253-257 -- taken even if the line search rejected it
+    p.status = TFMPC_ST_CONVERGED; p.phase = PH_DONE;
+    return true;
+  }
+  if (accept) {  // :259-266
+    p.delta = fmin(1.0 / o.delta_0, p.delta / o.delta_0);
+    p.mu = p.mu * p.delta * (double)(p.mu * p.delta > o.mu_min);
+    p.guard = 0;
+    if (p.iteration + 1 >= o.max_iterations) { p.status = TFMPC_ST_MAXITER; p.phase = PH_DONE; }  // `for iteration in t` exhausted (:227)
+    else p.iteration++;
+    return true;
+  }
+  p.delta = fmax(o.delta_0, p.delta * o.delta_0);  // :267-270, then redo the backward pass on the same linearisation
+  p.mu = fmax(o.mu_min, p.mu * p.delta);
+  if (++p.guard > 200) { p.status = TFMPC_ST_REGLOOP; p.phase = PH_DONE; }
+  return false;
+}
+
+// Sequential composition (host emulation / documentation of the control flow): X[0..1], U[0..1] ping-pong.
 template <int KIND, int N, int M>
 HD int solve_one(const EnvSmall &e, const IlqrOpts &o, int T, const View X[2], const View U[2], const View &Kv, const View &kv,
                  int32_t *stats) {
-  double mu = 0.0, delta = 1.0;  // python floats in the reference, ilqr.py:215-216
-  int cur = 0, n_bwd = 0, n_fwd = 0, status = TFMPC_ST_MAXITER, iteration = 0;
+  Prob p;
+  prob_init(p);
   const View none = {nullptr, 0};
-  for (iteration = 0; iteration < o.max_iterations; iteration++) {
-    bool converged = false;
-    int guard = 0;
-    for (;;) {
-      real J_hat, dV1, dV2, gsum;
-      double mu_l = mu, delta_l = delta;  // _backward's bump is local, ilqr.py:308-309,315
-      int bst, tries = 0;
-      for (;;) {
-        bst = backward_pass<KIND, N, M>(e, T, X[cur], U[cur], (real)mu_l, Kv, kv, J_hat, dV1, dV2, gsum);
-        n_bwd++;
-        if (bst != 1 || ++tries > 200) break;
-        delta_l = fmax(o.delta_0, delta_l * o.delta_0);
-        mu_l = fmax(o.mu_min, mu_l * delta_l);
-      }
-      if (bst) { status = TFMPC_ST_NONPD; converged = true; break; }
-      real g = gsum / (real)T;  // :243
-      if (!(g == g)) { status = TFMPC_ST_NAN; converged = true; break; }
-      if (g < o.atol) { status = TFMPC_ST_CONVERGED; converged = true; break; }  // :245-248
-      bool accept = false;
-      real residual = 0;
-      for (int ai = 0; ai < N_ALPHA; ai++) {  // :322
-        real alpha = o.alphas[ai], J;
-        forward_pass<KIND, N, M>(e, T, X[cur], U[cur], Kv, kv, alpha, X[cur ^ 1], U[cur ^ 1], none, J, residual);
-        n_fwd++;
-        real delta_J = -alpha * (dV1 + alpha * dV2);  // :339
-        real dcost = J_hat - J;
-        real z = (delta_J > 0) ? dcost / delta_J : r_sgn(dcost);  // :342-346
-        if (z >= o.c1) { accept = true; break; }  // :351
-      }
-      if (residual < o.atol) {  // :253-257 (the candidate is taken even if it was rejected)
-        status = TFMPC_ST_CONVERGED; converged = true; cur ^= 1;
-        break;
-      }
-      if (accept) {  // :259-266
-        delta = fmin(1.0 / o.delta_0, delta / o.delta_0);
-        mu = mu * delta * (double)(mu * delta > o.mu_min);
-        cur ^= 1;
-        break;
-      }
-      delta = fmax(o.delta_0, delta * o.delta_0);  // :267-270
-      mu = fmax(o.mu_min, mu * delta);
-      if (++guard > 200) { status = TFMPC_ST_REGLOOP; converged = true; break; }
+  while (p.phase != PH_DONE) {
+    tick_backward<KIND, N, M>(e, o, T, X[p.cur], U[p.cur], Kv, kv, p);
+    if (p.phase == PH_DONE) break;
+    bool accept = false;
+    real residual = 0;
+    int rollouts = 0;
+    for (int ai = 0; ai < N_ALPHA && !accept; ai++) {  // :322 first-accept backtracking
+      real J;
+      forward_pass<KIND, N, M>(e, T, X[p.cur], U[p.cur], Kv, kv, o.alphas[ai], X[p.cur ^ 1], U[p.cur ^ 1], none, J, residual);
+      rollouts++;
+      accept = ls_accepts(o, o.alphas[ai], p.J_hat, p.dV1, p.dV2, J);
     }
-    if (converged) break;
+    if (tick_finish(o, accept, residual, rollouts, p)) p.cur ^= 1;
   }
-  if (iteration >= o.max_iterations) iteration = o.max_iterations - 1;
-  stats[0] = iteration; stats[1] = n_bwd; stats[2] = n_fwd; stats[3] = status;
-  return cur;
+  stats[0] = p.iteration; stats[1] = p.n_bwd; stats[2] = p.n_fwd; stats[3] = p.status;
+  return p.cur;
 }

@@ -27,25 +27,26 @@ static void fill_env(EnvSmall &s, int kind, int n, int nz, const double *p) {
 template <int KIND, int N, int M>
 static void run(const EnvSmall &e, const IlqrOpts &o, int64_t B, int T, const real *x0, const real *u_init, real *states, real *actions,
                 real *costs, int32_t *stats) {
-  const int64_t S = (B + 31) / 32 * 32, nx = (int64_t)(T + 1) * N, nu = (int64_t)T * M;
-  std::vector<real> ws((size_t)(2 * (nx + nu) + nu * N + nu) * S);
+  // same vector-record workspace addressing as the CUDA solve kernels (chunk-major, slot fastest)
+  const int64_t S = (B + 31) / 32 * 32;
+  const int64_t nomch = (int64_t)(T + 1) * VecTraj<N, M>::CH, gch = (int64_t)T * VecGain<N, M>::CH;
+  std::vector<R4> ws((size_t)(2 * nomch + gch) * S);
+  const int64_t nx = (int64_t)(T + 1) * N, nu = (int64_t)T * M;
   for (int64_t b = 0; b < B; b++) {
-    real *base = ws.data() + b;
-    View X[2] = {{base, S}, {base + (nx + nu) * S, S}};
-    View U[2] = {{base + nx * S, S}, {base + (2 * nx + nu) * S, S}};
-    View Kv = {base + 2 * (nx + nu) * S, S}, kv = {base + (2 * (nx + nu) + nu * N) * S, S}, none = {nullptr, 0};
-    real x[N];
-    for (int i = 0; i < N; i++) x[i] = x0[b * N + i];
-    CView Ui = {u_init + b * nu, 1};
-    start_pass<KIND, N, M>(e, T, x, Ui, X[0], U[0], none);
-    int cur = solve_one<KIND, N, M>(e, o, T, X, U, Kv, kv, stats + b * 4);
-    real u[M];
+    VecTraj<N, M> traj[2] = {{ws.data() + b, S}, {ws.data() + nomch * S + b, S}};
+    VecGain<N, M> gain = {ws.data() + 2 * nomch * S + b, S};
+    const CostSink none = {nullptr, 0};
+    start_pass<KIND, N, M>(e, T, x0 + b * N, u_init + b * nu, traj[0], none);
+    int cur = solve_one<KIND, N, M>(e, o, T, traj, gain, stats + b * 4);
+    real x[N], u[M];
     for (int t = 0; t < T; t++) {
-      for (int i = 0; i < N; i++) { x[i] = X[cur](t * N + i); states[b * nx + t * N + i] = x[i]; }
-      for (int i = 0; i < M; i++) { u[i] = U[cur](t * M + i); actions[b * nu + t * M + i] = u[i]; }
+      traj[cur].load_xu(t, x, u);
+      for (int i = 0; i < N; i++) states[b * nx + t * N + i] = x[i];
+      for (int i = 0; i < M; i++) actions[b * nu + t * M + i] = u[i];
       costs[b * (T + 1) + t] = env_cost<KIND, N, M>(e, x, u);
     }
-    for (int i = 0; i < N; i++) { x[i] = X[cur](T * N + i); states[b * nx + T * N + i] = x[i]; }
+    traj[cur].load_x(T, x);
+    for (int i = 0; i < N; i++) states[b * nx + T * N + i] = x[i];
     costs[b * (T + 1) + T] = env_final_cost<KIND, N, M>(e, x);
   }
 }

@@ -7,6 +7,8 @@
 // workspace ws[row][slot] with the problem slot fastest, so the 32 lanes of a warp read and
 // write 32 consecutive words (one 128-byte line) for every row they touch.
 #include <algorithm>
+#include <atomic>
+#include <mutex>
 
 #include "small_core.cuh"
 
@@ -23,9 +25,9 @@ __global__ void __launch_bounds__(kThreads) k_start(EnvSmall e, int64_t B, int T
   real x[N];
 #pragma unroll
   for (int i = 0; i < N; i++) x[i] = x0[b * N + i];
-  CView Ui = {u_init + b * T * M, 1};
-  View Xo = {states + b * (T + 1) * N, 1}, Uo = {actions + b * T * M, 1}, Co = {costs + b * (T + 1), 1};
-  start_pass<KIND, N, M>(e, T, x, Ui, Xo, Uo, Co);
+  StridedTraj<N, M> out = {states + b * (T + 1) * N, actions + b * T * M, 1};
+  CostSink Co = {costs + b * (T + 1), 1};
+  start_pass<KIND, N, M>(e, T, x, u_init + b * T * M, out, Co);
 }
 
 template <int KIND, int N, int M>
@@ -35,10 +37,10 @@ __global__ void __launch_bounds__(kThreads) k_backward(EnvSmall e, int64_t B, in
                                                        real *__restrict__ dV2, int32_t *__restrict__ status) {
   int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
-  CView X = {states + b * (T + 1) * N, 1}, U = {actions + b * T * M, 1};
-  View Kv = {K + b * T * M * N, 1}, kv = {k + b * T * M, 1};
+  StridedTraj<N, M> nom = {const_cast<real *>(states) + b * (T + 1) * N, const_cast<real *>(actions) + b * T * M, 1};
+  StridedGain<N, M> gain = {K + b * T * M * N, k + b * T * M, 1};
   real Jb, d1, d2, g;
-  int st = backward_pass<KIND, N, M>(e, T, X, U, mu, Kv, kv, Jb, d1, d2, g);
+  int st = backward_pass<KIND, N, M>(e, T, nom, mu, gain, Jb, d1, d2, g);
   J[b] = Jb; dV1[b] = d1; dV2[b] = d2;
   if (status) status[b] = st;
 }
@@ -51,10 +53,12 @@ __global__ void __launch_bounds__(kThreads) k_forward(EnvSmall e, int64_t B, int
                                                       real *__restrict__ residual) {
   int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
-  CView X = {states + b * (T + 1) * N, 1}, U = {actions + b * T * M, 1}, Kv = {K + b * T * M * N, 1}, kv = {k + b * T * M, 1};
-  View Xo = {xs + b * (T + 1) * N, 1}, Uo = {us + b * T * M, 1}, Co = {cs + b * (T + 1), 1};
+  StridedTraj<N, M> nom = {const_cast<real *>(states) + b * (T + 1) * N, const_cast<real *>(actions) + b * T * M, 1};
+  StridedGain<N, M> gain = {const_cast<real *>(K) + b * T * M * N, const_cast<real *>(k) + b * T * M, 1};
+  StridedTraj<N, M> out = {xs + b * (T + 1) * N, us + b * T * M, 1};
+  CostSink Co = {cs + b * (T + 1), 1};
   real Jb, res;
-  forward_pass<KIND, N, M>(e, T, X, U, Kv, kv, alpha, Xo, Uo, Co, Jb, res);
+  forward_pass<KIND, N, M>(e, T, nom, gain, alpha, out, Co, Jb, res);
   J[b] = Jb; residual[b] = res;
 }
 
@@ -76,21 +80,22 @@ constexpr int GA = 4;            // line-search lanes (and candidate buffers) pe
 constexpr int NBUF = 1 + GA;
 constexpr int kExtraTicks = 24;  // ticks beyond max_iterations available to regularisation retries (ilqr.py:267-270)
 
-struct WS {  // carve-up of the workspace (all arrays struct-of-arrays, slot fastest)
+struct WS {  // carve-up of the workspace
   int *count;                    // [2] active counts (ping-pong)
   int *list[2];                  // [S] active problem slots
   int *iteration, *n_bwd, *n_fwd, *status, *cur, *phase, *guard;
   double *mu, *delta;
   real *J_hat, *dV1, *dV2;
-  real *traj;                    // NBUF x (nx + nu) rows
-  real *K, *k, *cost;            // nu*N, nu, T+1 rows
-  int64_t S;
+  R4 *traj;                      // NBUF buffers x (T+1) records x CHn chunks x S slots
+  R4 *gain;                      // T records x CHg chunks x S slots
+  real *cost;                    // (T+1) rows x S
+  int64_t S, traj_chunks;        // traj_chunks = (T+1) * CHn
 };
 
-__host__ __device__ inline int64_t ws_bytes_for(int64_t S, int T, int N, int M) {
-  int64_t nx = (int64_t)(T + 1) * N, nu = (int64_t)T * M;
-  int64_t rows = NBUF * (nx + nu) + nu * N + nu + (T + 1);
-  return 256 + S * (2 * 4 + 7 * 4 + 2 * 8 + 3 * (int64_t)sizeof(real)) + rows * S * (int64_t)sizeof(real) + 64;
+inline int64_t ws_bytes_for(int64_t S, int T, int N, int M) {
+  int64_t chn = (N + M + 3) / 4, chg = (M * N + M + 3) / 4;
+  int64_t vec = NBUF * (int64_t)(T + 1) * chn + (int64_t)T * chg;
+  return 256 + S * (2 * 4 + 7 * 4 + 2 * 8 + 3 * (int64_t)sizeof(real)) + 64 + vec * S * (int64_t)sizeof(R4) + (int64_t)(T + 1) * S * (int64_t)sizeof(real);
 }
 
 inline WS carve(void *ws, int64_t S, int T, int N, int M) {
@@ -106,22 +111,22 @@ inline WS carve(void *ws, int64_t S, int T, int N, int M) {
   for (int i = 0; i < 7; i++) { *ints[i] = (int *)p; p += S * 4; }
   real **reals[3] = {&w.J_hat, &w.dV1, &w.dV2};
   for (int i = 0; i < 3; i++) { *reals[i] = (real *)p; p += S * sizeof(real); }
-  p = (char *)(((uintptr_t)p + 15) & ~(uintptr_t)15);
-  int64_t nx = (int64_t)(T + 1) * N, nu = (int64_t)T * M;
-  w.traj = (real *)p; p += NBUF * (nx + nu) * S * sizeof(real);
-  w.K = (real *)p; p += nu * N * S * sizeof(real);
-  w.k = (real *)p; p += nu * S * sizeof(real);
+  p = (char *)(((uintptr_t)p + 63) & ~(uintptr_t)63);
+  int64_t chn = (N + M + 3) / 4, chg = (M * N + M + 3) / 4;
+  w.traj_chunks = (int64_t)(T + 1) * chn;
+  w.traj = (R4 *)p; p += NBUF * w.traj_chunks * S * sizeof(R4);
+  w.gain = (R4 *)p; p += (int64_t)T * chg * S * sizeof(R4);
   w.cost = (real *)p;
   return w;
 }
 
 template <int N, int M>
-__device__ __forceinline__ View bufX(const WS &w, int T, int buf, int64_t b) {
-  return View{w.traj + (int64_t)buf * ((int64_t)(T + 1) * N + (int64_t)T * M) * w.S + b, w.S};
+__device__ __forceinline__ VecTraj<N, M> buf_traj(const WS &w, int buf, int64_t b) {
+  return VecTraj<N, M>{w.traj + (int64_t)buf * w.traj_chunks * w.S + b, w.S};
 }
 template <int N, int M>
-__device__ __forceinline__ View bufU(const WS &w, int T, int buf, int64_t b) {
-  return View{w.traj + ((int64_t)buf * ((int64_t)(T + 1) * N + (int64_t)T * M) + (int64_t)(T + 1) * N) * w.S + b, w.S};
+__device__ __forceinline__ VecGain<N, M> buf_gain(const WS &w, int64_t b) {
+  return VecGain<N, M>{w.gain + b, w.S};
 }
 
 __device__ __forceinline__ void load_prob(const WS &w, int64_t b, Prob &p) {
@@ -144,9 +149,8 @@ __global__ void __launch_bounds__(kThreads) k_init(EnvSmall e, int64_t B, int T,
   real x[N];
 #pragma unroll
   for (int i = 0; i < N; i++) x[i] = x0[b * N + i];
-  CView Ui = {u_init + b * T * M, 1};
-  const View none = {nullptr, 0};
-  start_pass<KIND, N, M>(e, T, x, Ui, bufX<N, M>(w, T, 0, b), bufU<N, M>(w, T, 0, b), none);
+  const CostSink none = {nullptr, 0};
+  start_pass<KIND, N, M>(e, T, x, u_init + b * T * M, buf_traj<N, M>(w, 0, b), none);
 }
 
 template <int KIND, int N, int M>
@@ -158,8 +162,7 @@ __global__ void __launch_bounds__(kThreads) k_tick_backward(EnvSmall e, IlqrOpts
     const int64_t b = list[i];
     Prob p;
     load_prob(w, b, p);
-    View Kv = {w.K + b, w.S}, kv = {w.k + b, w.S};
-    tick_backward<KIND, N, M>(e, o, T, bufX<N, M>(w, T, p.cur, b), bufU<N, M>(w, T, p.cur, b), Kv, kv, p);
+    tick_backward<KIND, N, M>(e, o, T, buf_traj<N, M>(w, p.cur, b), buf_gain<N, M>(w, b), p);
     w.n_bwd[b] = p.n_bwd; w.status[b] = p.status; w.phase[b] = p.phase;
     w.J_hat[b] = p.J_hat; w.dV1[b] = p.dV1; w.dV2[b] = p.dV2;
   }
@@ -175,7 +178,7 @@ __global__ void __launch_bounds__(kThreads) k_tick_linesearch(EnvSmall e, IlqrOp
   const int lane = threadIdx.x & 31, la = lane % GA, sub = lane / GA;
   const int groups_per_warp = 32 / GA;
   const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-  const View none = {nullptr, 0};
+  const CostSink none = {nullptr, 0};
   for (int base = warp_global * groups_per_warp; base < cnt; base += nwarps * groups_per_warp) {  // warp-uniform trip count
     const int gi = base + sub;
     const bool valid = gi < cnt;
@@ -186,9 +189,10 @@ __global__ void __launch_bounds__(kThreads) k_tick_linesearch(EnvSmall e, IlqrOp
     bool searching = was_search, accept = false;
     real residual = 0;
     int rollouts = 0, cand = 0;
-    View Kv = {w.K + b, w.S}, kv = {w.k + b, w.S};
-    const View Xh = bufX<N, M>(w, T, p.cur, b), Uh = bufU<N, M>(w, T, p.cur, b);
+    const VecTraj<N, M> nom = buf_traj<N, M>(w, p.cur, b);
+    const VecGain<N, M> gain = buf_gain<N, M>(w, b);
     const int mybuf = la + (la >= p.cur ? 1 : 0);  // this lane's candidate buffer: the la-th buffer that is not the nominal
+    const VecTraj<N, M> mine = buf_traj<N, M>(w, mybuf, b);
     for (int pass = 0; pass < PASSES; pass++) {
       if (!__any_sync(FULL, searching)) break;
       const int ai = pass * GA + la;
@@ -197,7 +201,7 @@ __global__ void __launch_bounds__(kThreads) k_tick_linesearch(EnvSmall e, IlqrOp
       bool acc = false;
       if (run) {
         const real alpha = o.alphas[ai];
-        forward_pass<KIND, N, M>(e, T, Xh, Uh, Kv, kv, alpha, bufX<N, M>(w, T, mybuf, b), bufU<N, M>(w, T, mybuf, b), none, J, res);
+        forward_pass<KIND, N, M>(e, T, nom, gain, alpha, mine, none, J, res);
         acc = ls_accepts(o, alpha, p.J_hat, p.dV1, p.dV2, J);
       }
       const unsigned gm = (__ballot_sync(FULL, acc) >> (sub * GA)) & ((1u << GA) - 1u);
@@ -236,43 +240,47 @@ template <int KIND, int N, int M>
 __global__ void __launch_bounds__(kThreads) k_costs(EnvSmall e, int64_t B, int T, WS w, int32_t *__restrict__ stats) {
   int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
-  const int cur = w.cur[b];
-  const View X = bufX<N, M>(w, T, cur, b), U = bufU<N, M>(w, T, cur, b);
+  const VecTraj<N, M> nom = buf_traj<N, M>(w, w.cur[b], b);
   real x[N], u[M];
   for (int t = 0; t < T; t++) {
-#pragma unroll
-    for (int i = 0; i < N; i++) x[i] = X(t * N + i);
-#pragma unroll
-    for (int i = 0; i < M; i++) u[i] = U(t * M + i);
+    nom.load_xu(t, x, u);
     w.cost[(int64_t)t * w.S + b] = env_cost<KIND, N, M>(e, x, u);
   }
-#pragma unroll
-  for (int i = 0; i < N; i++) x[i] = X(T * N + i);
+  nom.load_x(T, x);
   w.cost[(int64_t)T * w.S + b] = env_final_cost<KIND, N, M>(e, x);
   int st = w.status[b];
   if (w.phase[b] != PH_DONE) st = TFMPC_ST_REGLOOP;  // ran out of ticks (more than kExtraTicks rejected line searches)
   reinterpret_cast<int4 *>(stats)[b] = make_int4(w.iteration[b], w.n_bwd[b], w.n_fwd[b], st);
 }
 
-// out[b][r] = src_b[r * S + b]: 32 x 32 tiles through shared memory so that both the struct-of-arrays reads and
-// the reference-layout writes are coalesced.  which: 0 = states, 1 = actions (buffer chosen per problem by cur), 2 = costs.
+// Workspace -> reference layouts.  out[b][r] for r < nrows: 32 x 32 tiles through shared memory so that both the
+// slot-fastest reads and the problem-major writes are coalesced.
+// which: 0 = states (r = t*N + i), 1 = actions (r = t*M + i) -- from the nominal buffer of each problem; 2 = costs.
 template <int N, int M>
 __global__ void __launch_bounds__(128) k_transpose_out(int64_t B, int T, WS w, int which, int nrows, real *__restrict__ out) {
   __shared__ real tile[4][32][33];
+  constexpr int CH = (N + M + 3) / 4;
   const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
   const int64_t slot0 = ((int64_t)blockIdx.x * 4 + wq) * 32;
   if (slot0 >= B) return;
   const int64_t b = slot0 + lane;
   const bool vb = b < B;
-  const real *src = w.cost + (vb ? b : 0);
-  if (which < 2 && vb) {
-    const int cur = w.cur[b];
-    src = (which == 0 ? bufX<N, M>(w, T, cur, b) : bufU<N, M>(w, T, cur, b)).p;
-  }
+  const real *rec = nullptr;
+  if (which < 2 && vb) rec = reinterpret_cast<const real *>(w.traj + (int64_t)w.cur[b] * w.traj_chunks * w.S + b);
   for (int r0 = 0; r0 < nrows; r0 += 32) {
 #pragma unroll 4
-    for (int rr = 0; rr < 32; rr++)
-      if (vb && r0 + rr < nrows) tile[wq][rr][lane] = src[(int64_t)(r0 + rr) * w.S];
+    for (int rr = 0; rr < 32; rr++) {
+      const int r = r0 + rr;
+      if (vb && r < nrows) {
+        real v;
+        if (which == 2) v = w.cost[(int64_t)r * w.S + b];
+        else {
+          const int t = which == 0 ? r / N : r / M, j = which == 0 ? r % N : N + r % M;
+          v = rec[((int64_t)(t * CH + (j >> 2)) * w.S) * 4 + (j & 3)];
+        }
+        tile[wq][rr][lane] = v;
+      }
+    }
     __syncwarp();
 #pragma unroll 4
     for (int ss = 0; ss < 32; ss++)
@@ -367,6 +375,30 @@ static int device_sms(int device) {
   return v;
 }
 
+// Straggler streams.  After kHeadTicks ticks most problems have converged and what remains is latency-bound: a few
+// problems, each tick a strictly sequential H-step sweep.  The tail of the launch sequence is therefore forked onto an
+// internal HIGH-PRIORITY stream (event fork / join, so the caller's stream still observes one ordered operation): when the
+// caller keeps several batches in flight on different streams, the tiny high-priority tail kernels of one batch slip in
+// between the large head kernels of the next instead of queueing behind them (measured: without priorities concurrent
+// full-size solves do not overlap at all, because the head grids monopolise CTA dispatch).
+constexpr int kHeadTicks = 24;
+constexpr int kTailStreams = 8;
+
+static cudaStream_t tail_stream(int device) {
+  static cudaStream_t pool[16][kTailStreams] = {};
+  static std::atomic<unsigned> rr[16];
+  static std::mutex mu;
+  if (device < 0 || device >= 16) return nullptr;
+  unsigned i = rr[device].fetch_add(1) % kTailStreams;
+  std::lock_guard<std::mutex> g(mu);
+  if (!pool[device][i]) {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);  // hi = numerically lowest = greatest priority
+    if (cudaStreamCreateWithPriority(&pool[device][i], cudaStreamNonBlocking, hi) != cudaSuccess) { cudaGetLastError(); pool[device][i] = nullptr; }
+  }
+  return pool[device][i];
+}
+
 template <int KIND, int N, int M>
 static int solve_launch(const tfmpc_env *e, int64_t B, int T, const real *x0, const real *u_init, const IlqrOpts &o, real *states,
                         real *actions, real *costs, int32_t *stats, void *ws, cudaStream_t s) {
@@ -377,16 +409,41 @@ static int solve_launch(const tfmpc_env *e, int64_t B, int T, const real *x0, co
   // persistent-style grids: enough threads for every active problem (x GA lanes), capped at a few waves
   const unsigned g_bwd = (unsigned)std::min<int64_t>(gB, (int64_t)sms * 16);
   const unsigned g_ls = (unsigned)std::min<int64_t>((B * GA + kThreads - 1) / kThreads, (int64_t)sms * 16);
+  // tail: one CTA per SM is plenty for the stragglers (grid-stride loops keep it correct for any count)
+  const unsigned g_bwd_t = std::min<unsigned>(g_bwd, (unsigned)sms), g_ls_t = std::min<unsigned>(g_ls, (unsigned)sms * 2);
   const int ticks = o.max_iterations + kExtraTicks;
-  for (int t = 0; t < ticks; t++) {
+  const int head = std::min(ticks, kHeadTicks);
+  for (int t = 0; t < head; t++) {
     k_tick_backward<KIND, N, M><<<g_bwd, kThreads, 0, s>>>(e->es, o, T, w, t & 1);
     k_tick_linesearch<KIND, N, M><<<g_ls, kThreads, 0, s>>>(e->es, o, T, w, t & 1);
   }
-  k_costs<KIND, N, M><<<gB, kThreads, 0, s>>>(e->es, B, T, w, stats);
+  cudaStream_t ts = (ticks > head) ? tail_stream(e->device) : nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+  if (ts) {
+    if (cudaEventCreateWithFlags(&fork, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&join, cudaEventDisableTiming) != cudaSuccess) {
+      cudaGetLastError();
+      if (fork) cudaEventDestroy(fork);
+      fork = join = nullptr;
+      ts = nullptr;
+    }
+  }
+  cudaStream_t q = ts ? ts : s;
+  if (ts) { cudaEventRecord(fork, s); cudaStreamWaitEvent(ts, fork, 0); }
+  for (int t = head; t < ticks; t++) {
+    k_tick_backward<KIND, N, M><<<g_bwd_t, kThreads, 0, q>>>(e->es, o, T, w, t & 1);
+    k_tick_linesearch<KIND, N, M><<<g_ls_t, kThreads, 0, q>>>(e->es, o, T, w, t & 1);
+  }
+  k_costs<KIND, N, M><<<gB, kThreads, 0, q>>>(e->es, B, T, w, stats);
   const unsigned gT = (unsigned)((B + 127) / 128);
-  k_transpose_out<N, M><<<gT, 128, 0, s>>>(B, T, w, 0, (T + 1) * N, states);
-  k_transpose_out<N, M><<<gT, 128, 0, s>>>(B, T, w, 1, T * M, actions);
-  k_transpose_out<N, M><<<gT, 128, 0, s>>>(B, T, w, 2, T + 1, costs);
+  k_transpose_out<N, M><<<gT, 128, 0, q>>>(B, T, w, 0, (T + 1) * N, states);
+  k_transpose_out<N, M><<<gT, 128, 0, q>>>(B, T, w, 1, T * M, actions);
+  k_transpose_out<N, M><<<gT, 128, 0, q>>>(B, T, w, 2, T + 1, costs);
+  if (ts) {
+    cudaEventRecord(join, ts);
+    cudaStreamWaitEvent(s, join, 0);
+    cudaEventDestroy(fork);   // released by the runtime once the recorded work has completed
+    cudaEventDestroy(join);
+  }
   tfmpc_count_launch(2 * ticks + 4);
   return TFMPC_OK;
 }

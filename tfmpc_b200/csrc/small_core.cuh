@@ -467,48 +467,171 @@ HD int backward_step(const EnvSmall &e, const Lin<N, M> &L, const real *u, real 
   return status;
 }
 
-// ------------------------------------------------------------------ strided views
-// A problem's arrays are addressed as base[row * stride]: stride 1 = the reference's dense
-// [T, n] layout of one problem; stride S = struct-of-arrays workspace with the problem (slot)
-// index fastest, so that the 32 lanes of a warp touch 32 consecutive words.
-struct View {
+// ------------------------------------------------------------------ trajectory / gain accessors
+// The passes below read and write whole per-timestep RECORDS through two accessor concepts:
+//   trajectory:  load_xu(t, x, u)  load_x(t, x)  store_xu(t, x, u)  store_x(t, x)      (t = T holds x only)
+//   gains:       load(t, K, k)  store(t, K, k)
+// Two implementations:
+//  * Strided*  -- plain arrays addressed as base[row * stride]; stride 1 = the reference's dense [T, n] layout of one
+//                 problem (stage kernels, host emulation).
+//  * Vec*      -- the solve workspace: 16-byte (4 x real) chunks, chunk-major then problem slot, i.e.
+//                 chunk[(t * CH + c) * S + slot].  One timestep of one problem is CH consecutive-in-t vector words, so a
+//                 thread moves it with CH 128-bit accesses (LDG.128 / STG.128), a warp of adjacent slots covers 512
+//                 contiguous bytes per access, and a lone problem still uses half of every 32-byte sector it touches
+//                 (the scalar struct-of-arrays layout used 4 of 32 bytes once the active list is no longer contiguous).
+struct alignas(4 * sizeof(real)) R4 { real v[4]; };
+
+template <int N, int M>
+struct StridedTraj {
+  real *X, *U;       // X[(t * N + i) * stride], U[(t * M + i) * stride]
+  int64_t stride;
+  HD void load_xu(int t, real *x, real *u) const {
+#pragma unroll
+    for (int i = 0; i < N; i++) x[i] = X[(int64_t)(t * N + i) * stride];
+#pragma unroll
+    for (int i = 0; i < M; i++) u[i] = U[(int64_t)(t * M + i) * stride];
+  }
+  HD void load_x(int t, real *x) const {
+#pragma unroll
+    for (int i = 0; i < N; i++) x[i] = X[(int64_t)(t * N + i) * stride];
+  }
+  HD void store_xu(int t, const real *x, const real *u) const {
+#pragma unroll
+    for (int i = 0; i < N; i++) X[(int64_t)(t * N + i) * stride] = x[i];
+#pragma unroll
+    for (int i = 0; i < M; i++) U[(int64_t)(t * M + i) * stride] = u[i];
+  }
+  HD void store_x(int t, const real *x) const {
+#pragma unroll
+    for (int i = 0; i < N; i++) X[(int64_t)(t * N + i) * stride] = x[i];
+  }
+};
+
+template <int N, int M>
+struct StridedGain {
+  real *K, *k;       // K[(t * M * N + i) * stride], k[(t * M + i) * stride]
+  int64_t stride;
+  HD void load(int t, real *Kt, real *kt) const {
+#pragma unroll
+    for (int i = 0; i < M * N; i++) Kt[i] = K[(int64_t)(t * M * N + i) * stride];
+#pragma unroll
+    for (int i = 0; i < M; i++) kt[i] = k[(int64_t)(t * M + i) * stride];
+  }
+  HD void store(int t, const real *Kt, const real *kt) const {
+#pragma unroll
+    for (int i = 0; i < M * N; i++) K[(int64_t)(t * M * N + i) * stride] = Kt[i];
+#pragma unroll
+    for (int i = 0; i < M; i++) k[(int64_t)(t * M + i) * stride] = kt[i];
+  }
+};
+
+template <int CNT>
+HD void vec_load(const R4 *base, int64_t S, int t, real *out) {  // CNT reals of record t
+  constexpr int CH = (CNT + 3) / 4;
+#pragma unroll
+  for (int c = 0; c < CH; c++) {
+    const R4 r = base[(int64_t)(t * CH + c) * S];
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+      if (c * 4 + j < CNT) out[c * 4 + j] = r.v[j];
+  }
+}
+template <int CNT>
+HD void vec_store(R4 *base, int64_t S, int t, const real *in) {
+  constexpr int CH = (CNT + 3) / 4;
+#pragma unroll
+  for (int c = 0; c < CH; c++) {
+    R4 r;
+#pragma unroll
+    for (int j = 0; j < 4; j++) r.v[j] = (c * 4 + j < CNT) ? in[c * 4 + j] : (real)0;
+    base[(int64_t)(t * CH + c) * S] = r;
+  }
+}
+
+template <int N, int M>
+struct VecTraj {     // record t = [x (N), u (M)]
+  R4 *base;          // already offset to this problem's slot
+  int64_t S;
+  static constexpr int CH = (N + M + 3) / 4;
+  HD void load_xu(int t, real *x, real *u) const {
+    real r[N + M];
+    vec_load<N + M>(base, S, t, r);
+#pragma unroll
+    for (int i = 0; i < N; i++) x[i] = r[i];
+#pragma unroll
+    for (int i = 0; i < M; i++) u[i] = r[N + i];
+  }
+  HD void load_x(int t, real *x) const {
+    real r[N + M];
+    vec_load<N + M>(base, S, t, r);
+#pragma unroll
+    for (int i = 0; i < N; i++) x[i] = r[i];
+  }
+  HD void store_xu(int t, const real *x, const real *u) const {
+    real r[N + M];
+#pragma unroll
+    for (int i = 0; i < N; i++) r[i] = x[i];
+#pragma unroll
+    for (int i = 0; i < M; i++) r[N + i] = u[i];
+    vec_store<N + M>(base, S, t, r);
+  }
+  HD void store_x(int t, const real *x) const {
+    real r[N + M];
+#pragma unroll
+    for (int i = 0; i < N; i++) r[i] = x[i];
+#pragma unroll
+    for (int i = 0; i < M; i++) r[N + i] = 0;
+    vec_store<N + M>(base, S, t, r);
+  }
+};
+
+template <int N, int M>
+struct VecGain {     // record t = [K (M*N), k (M)]
+  R4 *base;
+  int64_t S;
+  static constexpr int CH = (M * N + M + 3) / 4;
+  HD void load(int t, real *Kt, real *kt) const {
+    real r[M * N + M];
+    vec_load<M * N + M>(base, S, t, r);
+#pragma unroll
+    for (int i = 0; i < M * N; i++) Kt[i] = r[i];
+#pragma unroll
+    for (int i = 0; i < M; i++) kt[i] = r[M * N + i];
+  }
+  HD void store(int t, const real *Kt, const real *kt) const {
+    real r[M * N + M];
+#pragma unroll
+    for (int i = 0; i < M * N; i++) r[i] = Kt[i];
+#pragma unroll
+    for (int i = 0; i < M; i++) r[M * N + i] = kt[i];
+    vec_store<M * N + M>(base, S, t, r);
+  }
+};
+
+// optional per-timestep cost sink (stage API); p == nullptr discards
+struct CostSink {
   real *p;
   int64_t stride;
-  HD real &operator()(int row) const { return p[(int64_t)row * stride]; }
-};
-struct CView {
-  const real *p;
-  int64_t stride;
-  HD real operator()(int row) const { return p[(int64_t)row * stride]; }
+  HD void put(int t, real c) const { if (p) p[(int64_t)t * stride] = c; }
 };
 
 // iLQR.backward over the whole horizon (ilqr.py:94-172), linearisation fused (ilqr.py:84-92).
 // Also accumulates sum_t max_i |k|/(|u|+1) for the g_norm test of ilqr.py:243.
-template <int KIND, int N, int M, class XV, class UV>
-HD int backward_pass(const EnvSmall &e, int T, const XV &X, const UV &U, real mu, const View &Kv, const View &kv, real &J, real &dV1,
-                     real &dV2, real &gsum) {
+template <int KIND, int N, int M, class TJ, class GN>
+HD int backward_pass(const EnvSmall &e, int T, const TJ &nom, real mu, const GN &gain, real &J, real &dV1, real &dV2, real &gsum) {
   real V_x[N], V_xx[N * N], x[N], u[M];
-#pragma unroll
-  for (int i = 0; i < N; i++) x[i] = X(T * N + i);
+  nom.load_x(T, x);
   env_final_quad<KIND, N, M>(e, x, J, V_x, V_xx);  // :101-104
   dV1 = 0; dV2 = 0; gsum = 0;
   int status = 0;
   real xn[N], un[M];
-#pragma unroll
-  for (int i = 0; i < N; i++) xn[i] = X((T - 1) * N + i);
-#pragma unroll
-  for (int i = 0; i < M; i++) un[i] = U((T - 1) * M + i);
+  nom.load_xu(T - 1, xn, un);
   for (int t = T - 1; t >= 0; t--) {
 #pragma unroll
     for (int i = 0; i < N; i++) x[i] = xn[i];
 #pragma unroll
     for (int i = 0; i < M; i++) u[i] = un[i];
-    if (t > 0) {  // software prefetch of the next (earlier) timestep
-#pragma unroll
-      for (int i = 0; i < N; i++) xn[i] = X((t - 1) * N + i);
-#pragma unroll
-      for (int i = 0; i < M; i++) un[i] = U((t - 1) * M + i);
-    }
+    nom.load_xu(t > 0 ? t - 1 : 0, xn, un);  // software prefetch of the next (earlier) timestep
     Lin<N, M> L;
     env_linearize<KIND, N, M>(e, x, u, L);
     real K[M * N], k[M];
@@ -520,39 +643,34 @@ HD int backward_pass(const EnvSmall &e, int T, const XV &X, const UV &U, real mu
     for (int i = 0; i < M; i++) {
       real v = r_abs(k[i]) / (r_abs(u[i]) + (real)1.0);
       mx = (i == 0 || v > mx) ? v : mx;
-      kv(t * M + i) = k[i];
     }
     gsum += mx;
-#pragma unroll
-    for (int i = 0; i < M * N; i++) Kv(t * M * N + i) = K[i];
+    gain.store(t, K, k);
   }
   return status;
 }
 
-// iLQR.forward (ilqr.py:174-212).  cs may be a null view (p == nullptr) when costs are not wanted.
-// The nominal operands of step t+1 are loaded while step t computes (explicit software prefetch): in the
-// line search this loop is bound by memory latency otherwise.
-template <int KIND, int N, int M, class XV, class UV, class KV>
-HD void forward_pass(const EnvSmall &e, int T, const XV &Xh, const UV &Uh, const KV &Kv, const KV &kv, real alpha, const View &Xo,
-                     const View &Uo, const View &Co, real &J, real &residual) {
+// iLQR.forward (ilqr.py:174-212).  The nominal records and gains are loaded TWO steps ahead of their use
+// (explicit software prefetch, a 2-deep register ring): one step of arithmetic is shorter than a DRAM / far-L2
+// round trip, and in the line search this loop is otherwise bound by exactly that latency.
+template <int KIND, int N, int M, class TJ, class GN, class TO>
+HD void forward_pass(const EnvSmall &e, int T, const TJ &nom, const GN &gain, real alpha, const TO &out, const CostSink &Co, real &J,
+                     real &residual) {
   real x[N], u[M], xn[N];
-  real xh[N], uh[M], Kt[M * N], kt[M];
+  real xh[N], uh[M], Kt[M * N], kt[M];        // step t
+  real xh1[N], uh1[M], K1[M * N], k1[M];      // step t+1
   J = 0; residual = 0;
+  nom.load_xu(0, xh, uh);
+  gain.load(0, Kt, kt);
+  nom.load_xu(T > 1 ? 1 : 0, xh1, uh1);
+  gain.load(T > 1 ? 1 : 0, K1, k1);
 #pragma unroll
-  for (int i = 0; i < N; i++) { xh[i] = Xh(i); x[i] = xh[i]; Xo(i) = x[i]; }
-#pragma unroll
-  for (int i = 0; i < M; i++) { uh[i] = Uh(i); kt[i] = kv(i); }
-#pragma unroll
-  for (int i = 0; i < M * N; i++) Kt[i] = Kv(i);
+  for (int i = 0; i < N; i++) x[i] = xh[i];
   for (int t = 0; t < T; t++) {
-    real xh_n[N], uh_n[M], K_n[M * N], k_n[M];
-    const int tn = (t + 1 < T) ? t + 1 : t;  // last step re-reads itself (harmless) instead of branching
-#pragma unroll
-    for (int i = 0; i < N; i++) xh_n[i] = Xh(tn * N + i);
-#pragma unroll
-    for (int i = 0; i < M; i++) { uh_n[i] = Uh(tn * M + i); k_n[i] = kv(tn * M + i); }
-#pragma unroll
-    for (int i = 0; i < M * N; i++) K_n[i] = Kv(tn * M * N + i);
+    real xh2[N], uh2[M], K2[M * N], k2[M];    // step t+2, in flight while steps t and t+1 compute
+    const int t2 = (t + 2 < T) ? t + 2 : T - 1;  // the last steps re-read the final record (harmless) instead of branching
+    nom.load_xu(t2, xh2, uh2);
+    gain.load(t2, K2, k2);
 #pragma unroll
     for (int i = 0; i < M; i++) {
       real s = 0;
@@ -564,37 +682,39 @@ HD void forward_pass(const EnvSmall &e, int T, const XV &Xh, const UV &Uh, const
     }
     real c = env_cost<KIND, N, M>(e, x, u);
     env_step<KIND, N, M>(e, x, u, xn);
-#pragma unroll
-    for (int i = 0; i < M; i++) Uo(t * M + i) = u[i];
-    if (Co.p) Co(t) = c;
+    out.store_xu(t, x, u);
+    Co.put(t, c);
     J += c;
 #pragma unroll
-    for (int i = 0; i < N; i++) { x[i] = xn[i]; Xo((t + 1) * N + i) = x[i]; xh[i] = xh_n[i]; }
+    for (int i = 0; i < N; i++) { x[i] = xn[i]; xh[i] = xh1[i]; xh1[i] = xh2[i]; }
 #pragma unroll
-    for (int i = 0; i < M; i++) { uh[i] = uh_n[i]; kt[i] = k_n[i]; }
+    for (int i = 0; i < M; i++) { uh[i] = uh1[i]; kt[i] = k1[i]; uh1[i] = uh2[i]; k1[i] = k2[i]; }
 #pragma unroll
-    for (int i = 0; i < M * N; i++) Kt[i] = K_n[i];
+    for (int i = 0; i < M * N; i++) { Kt[i] = K1[i]; K1[i] = K2[i]; }
   }
+  out.store_x(T, x);
   real cf = env_final_cost<KIND, N, M>(e, x);
-  if (Co.p) Co(T) = cf;
+  Co.put(T, cf);
   J += cf;
 }
 
-// iLQR.start with pinned actions (ilqr.py:53-82)
-template <int KIND, int N, int M, class UV>
-HD void start_pass(const EnvSmall &e, int T, const real *x0, const UV &Ui, const View &Xo, const View &Uo, const View &Co) {
+// iLQR.start with pinned actions (ilqr.py:53-82); u_init[t * M + i] is the reference's dense layout
+template <int KIND, int N, int M, class TO>
+HD void start_pass(const EnvSmall &e, int T, const real *x0, const real *u_init, const TO &out, const CostSink &Co) {
   real x[N], u[M], xn[N];
 #pragma unroll
-  for (int i = 0; i < N; i++) { x[i] = x0[i]; Xo(i) = x[i]; }
+  for (int i = 0; i < N; i++) x[i] = x0[i];
   for (int t = 0; t < T; t++) {
 #pragma unroll
-    for (int i = 0; i < M; i++) { u[i] = Ui(t * M + i); Uo(t * M + i) = u[i]; }
-    if (Co.p) Co(t) = env_cost<KIND, N, M>(e, x, u);
+    for (int i = 0; i < M; i++) u[i] = u_init[t * M + i];
+    Co.put(t, env_cost<KIND, N, M>(e, x, u));
     env_step<KIND, N, M>(e, x, u, xn);
+    out.store_xu(t, x, u);
 #pragma unroll
-    for (int i = 0; i < N; i++) { x[i] = xn[i]; Xo((t + 1) * N + i) = x[i]; }
+    for (int i = 0; i < N; i++) x[i] = xn[i];
   }
-  if (Co.p) Co(T) = env_final_cost<KIND, N, M>(e, x);
+  out.store_x(T, x);
+  Co.put(T, env_final_cost<KIND, N, M>(e, x));
 }
 
 // ------------------------------------------------------------------ the solve, as per-problem TICKS
@@ -617,13 +737,13 @@ HD void prob_init(Prob &p) {
 }
 
 // _backward (:285-315) + the g_norm test (:243-248).  Leaves p.phase = PH_SEARCH if a line search must follow.
-template <int KIND, int N, int M>
-HD void tick_backward(const EnvSmall &e, const IlqrOpts &o, int T, const View &X, const View &U, const View &Kv, const View &kv, Prob &p) {
+template <int KIND, int N, int M, class TJ, class GN>
+HD void tick_backward(const EnvSmall &e, const IlqrOpts &o, int T, const TJ &nom, const GN &gain, Prob &p) {
   real gsum;
   double mu_l = p.mu, delta_l = p.delta;  // the retry bump is local, ilqr.py:308-309,315
   int bst, tries = 0;
   for (;;) {
-    bst = backward_pass<KIND, N, M>(e, T, X, U, (real)mu_l, Kv, kv, p.J_hat, p.dV1, p.dV2, gsum);
+    bst = backward_pass<KIND, N, M>(e, T, nom, (real)mu_l, gain, p.J_hat, p.dV1, p.dV2, gsum);
     p.n_bwd++;
     if (bst != 1 || ++tries > 200) break;
     delta_l = fmax(o.delta_0, delta_l * o.delta_0);
@@ -667,22 +787,21 @@ HD bool tick_finish(const IlqrOpts &o, bool accept, real residual, int rollouts,
   return false;
 }
 
-// Sequential composition (host emulation / documentation of the control flow): X[0..1], U[0..1] ping-pong.
-template <int KIND, int N, int M>
-HD int solve_one(const EnvSmall &e, const IlqrOpts &o, int T, const View X[2], const View U[2], const View &Kv, const View &kv,
-                 int32_t *stats) {
+// Sequential composition (host emulation / documentation of the control flow): traj[0..1] ping-pong.
+template <int KIND, int N, int M, class TJ, class GN>
+HD int solve_one(const EnvSmall &e, const IlqrOpts &o, int T, const TJ traj[2], const GN &gain, int32_t *stats) {
   Prob p;
   prob_init(p);
-  const View none = {nullptr, 0};
+  const CostSink none = {nullptr, 0};
   while (p.phase != PH_DONE) {
-    tick_backward<KIND, N, M>(e, o, T, X[p.cur], U[p.cur], Kv, kv, p);
+    tick_backward<KIND, N, M>(e, o, T, traj[p.cur], gain, p);
     if (p.phase == PH_DONE) break;
     bool accept = false;
     real residual = 0;
     int rollouts = 0;
     for (int ai = 0; ai < N_ALPHA && !accept; ai++) {  // :322 first-accept backtracking
       real J;
-      forward_pass<KIND, N, M>(e, T, X[p.cur], U[p.cur], Kv, kv, o.alphas[ai], X[p.cur ^ 1], U[p.cur ^ 1], none, J, residual);
+      forward_pass<KIND, N, M>(e, T, traj[p.cur], gain, o.alphas[ai], traj[p.cur ^ 1], none, J, residual);
       rollouts++;
       accept = ls_accepts(o, o.alphas[ai], p.J_hat, p.dV1, p.dV2, J);
     }

@@ -370,7 +370,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="problems per GPU (default: the workload's BASELINE batch)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="problems in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--streams", type=int, default=4, help="CUDA streams the independent steps are pipelined over (1 = strictly sequential)")
+    ap.add_argument("--streams", type=int, default=8, help="CUDA streams the independent steps are pipelined over (1 = strictly sequential)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

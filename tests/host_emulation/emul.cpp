@@ -20,6 +20,9 @@ static void fill_env(EnvSmall &s, int kind, int n, int nz, const double *p) {
     for (int i = 0; i < 2; i++) { s.goal[i] = (real)p[i]; s.low[i] = (real)p[2 + i]; s.high[i] = (real)p[4 + i]; }
     for (int z = 0; z < nz; z++) { s.center[z][0] = (real)p[6 + 2 * z]; s.center[z][1] = (real)p[6 + 2 * z + 1]; s.decay[z] = (real)p[6 + 2 * nz + z]; }
   }
+  static real tab[QP_MAX_STEPS];
+  s.qp_klast = qp_step_table(tab);
+  s.qp_steps = tab;
   s.bounded = 1;
   for (int i = 0; i < n; i++) if (std::isinf((double)s.low[i]) || std::isinf((double)s.high[i])) s.bounded = 0;
 }

@@ -7,6 +7,9 @@ total cost and actions 1e-4 relative with the same iteration count (a +-1 differ
 a small fraction of problems and that fraction is asserted); the fp64 verification build is held
 to 1e-9.  Reservoir is chaotic (SURVEY finding 7): per-stage parity plus distributional parity.
 """
+import json
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -499,3 +502,90 @@ def test_full_size_large_env_properties(case):
     assert torch.max((nxt - xs[:, 1:]).abs() / (1 + xs[:, 1:].abs())) < 1e-5
     s0, a0, c0 = solver.start(x0, T, u_init=u0)
     assert torch.all(cs.sum(1) <= c0.sum(1) + 1e-5 * c0.sum(1).abs())
+
+
+# ------------------------------------------------------------------ callers of the path
+def test_mpc_runner_closed_loop_hvac_and_nav(tmp_path):
+    """MPC agent + Runner (reference agents/mpc.py:10-15, runners/__init__.py:14-43): shrinking-horizon re-solve at every
+    plant step.  Checked against the same loop driven with the oracle as the solver, with identical initial actions."""
+    from oracle import oracle
+    from tfmpc_b200 import agents, envs, runners
+    from tfmpc_b200.envs import synthetic
+    from tfmpc_b200.solvers.ilqr import iLQR
+    o = oracle.Oracle("f32")
+    for cfg, H in ((synthetic.hvac_grid_config(2, 3), 6), (synthetic.navigation_config(), 8)):
+        env = envs.make_env(cfg)
+        solver = iLQR(env)
+        x0 = np.asarray(cfg["initial_state"], dtype=np.float32)
+        controller = agents.MPC(solver, H, seed=123)
+        with runners.Runner(env, controller)(x0, H) as r:
+            traj = r.run()
+        assert traj.states.shape == (H + 1, env.state_size) and traj.actions.shape == (H, env.action_size) and traj.costs.shape == (H + 1,)
+        # replay with the oracle: same seeds -> same initial actions at every plant step
+        oenv = o.make_env(cfg)
+        state = x0.reshape(1, -1).astype(np.float32)
+        total = 0.0
+        for t in range(H):
+            u0 = _np(solver.initial_actions(1, H - t, seed=123 + t))
+            sol = o.ilqr_solve(oenv, state, u0)
+            action = sol["actions"][:, 0]
+            nxt, c, _ = o.env_eval(oenv, state, action)
+            assert np.allclose(traj.actions[t], action[0], atol=2e-3), (t, traj.actions[t], action[0])
+            total += float(c[0])
+            state = nxt
+        _, _, fc = o.env_eval(oenv, state, np.zeros_like(state))
+        total += float(fc[0])
+        assert abs(traj.total_cost - total) <= 2e-3 * abs(total)
+        assert len(controller.iterations) == H
+
+
+def test_launchers_and_csv(tmp_path):
+    """launchers.ilqr_run / online_ilqr_run (reference launchers/__init__.py:12-51): env JSON -> solve -> data.csv"""
+    import pandas as pd
+    from tfmpc_b200.envs import synthetic
+    from tfmpc_b200.launchers import ilqr_run, online_ilqr_run
+    path = tmp_path / "nav.json"
+    path.write_text(json.dumps(synthetic.navigation_config()))
+    env, traj = ilqr_run({"env": str(path), "horizon": 12, "logdir": str(tmp_path / "a"), "seed": 3})
+    df = pd.read_csv(tmp_path / "a" / "data.csv", index_col="Timestep")
+    assert list(df.columns) == ["x[1]", "x[2]", "u[1]", "u[2]", "costs"] and len(df) == 12
+    assert np.allclose(df["x[1]"].values, traj.states[1:, 0], atol=1e-5)
+    env, traj2 = online_ilqr_run({"env": str(path), "horizon": 5, "logdir": str(tmp_path / "b"), "seed": 3})
+    assert traj2.states.shape == (6, 2) and os.path.exists(tmp_path / "b" / "data.csv")
+
+
+def test_cli_commands(tmp_path):
+    """`tfmpc navlin` reproduces the v0.7.0-source numbers quoted in BASELINE.md; `tfmpc ilqr` writes its CSV."""
+    import subprocess
+    import sys
+    from tfmpc_b200.envs import synthetic
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cli = os.path.join(root, "scripts", "tfmpc.py")
+    out = subprocess.run([sys.executable, cli, "navlin", "-b", "5.0", "-hr", "10", "--", "0.0 0.0", "8.0 -9.0"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    assert "total=-1190.32" in out.stdout and "Steps" in out.stdout
+    out = subprocess.run([sys.executable, cli, "lqr", "-a", "2", "-hr", "10", "--", "-1.0 0.5 3.6"], capture_output=True, text=True)
+    assert out.returncode == 0 and "Trajectory(init=[-1.   0.5  3.6]" in out.stdout
+    path = tmp_path / "nav.json"
+    path.write_text(json.dumps(synthetic.navigation_config()))
+    out = subprocess.run([sys.executable, cli, "ilqr", str(path), "-hr", "10", "--logdir", str(tmp_path / "log"), "--seed", "0", "-ns", "2"],
+                         capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    assert out.stdout.count("Trajectory(init=") == 2 and os.path.exists(tmp_path / "log" / "run1" / "data.csv")
+
+
+def test_lqr_dump_load_roundtrip(tmp_path):
+    """reference tests/test_lqr.py:97-107"""
+    from tfmpc_b200 import envs
+    from tfmpc_b200.solvers.lqr import LQR
+    np.random.seed(0)
+    lq = envs.make_lqr(3, 2)
+    p = tmp_path / "lqr.json"
+    with open(p, "w") as fh:
+        lq.dump(fh)
+    with open(p) as fh:
+        lq2 = LQR.load(fh)
+    for k in ("F", "f", "C", "c"):
+        assert torch.equal(getattr(lq, k), getattr(lq2, k))
+    x0 = np.array([[-1.0], [0.5], [3.6]])
+    assert np.allclose(lq.solve(x0, 10).states, lq2.solve(x0, 10).states)

@@ -1,0 +1,67 @@
+"""World-size-2 gloo tests (CPU) of the host-side multi-GPU logic: contiguous sharding and the single end-of-solve
+all-gather.  The per-rank compute is stubbed by the CPU oracle here -- these tests cover
+the plumbing, the GPU tests cover the kernels."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def test_shard_range_partitions_the_batch():
+    from tfmpc_b200.sharding import shard_range
+    for B in (0, 1, 7, 8, 65536, 65537):
+        for world in (1, 2, 3, 8):
+            blocks = [shard_range(B, r, world) for r in range(world)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == B
+            assert all(blocks[i][1] == blocks[i + 1][0] for i in range(world - 1))
+            sizes = [hi - lo for lo, hi in blocks]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_range(4, 2, 2)
+
+
+def _worker(rank, world, port, B, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import oracle
+        from tfmpc_b200.envs import synthetic
+        from tfmpc_b200.sharding import gather_summaries, shard_range
+        cfg = synthetic.navlqr_config([5.5, -9.0], 5.0, -1.0, 1.0)
+        rng = np.random.RandomState(0)          # the same global batch on every rank
+        T = 10
+        x0 = synthetic.sample_x0(cfg, B, rng)
+        u0 = synthetic.sample_u_init([-1, -1], [1, 1], B, T, rng)
+        lo, hi = shard_range(B, rank, world)
+        o = oracle.Oracle("f32")
+        r = o.ilqr_solve(o.make_env(cfg), x0[lo:hi], u0[lo:hi], nthreads=1)     # stand-in for the per-GPU solve
+        cost, its, st = gather_summaries(torch.from_numpy(r["costs"].sum(1)), torch.from_numpy(r["iterations"]),
+                                         torch.from_numpy(r["status"]), B)
+        full = o.ilqr_solve(o.make_env(cfg), x0, u0, nthreads=1)
+        ok = (cost.shape[0] == B and np.allclose(cost.numpy(), full["costs"].sum(1)) and (its.numpy() == full["iterations"]).all()
+              and (st.numpy() == full["status"]).all())
+        ret[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("B", [8, 11])
+def test_sharded_solve_and_gather_world2(B):
+    world, port = 2, _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, port, B, ret), nprocs=world, join=True)
+    assert dict(ret) == {0: True, 1: True}

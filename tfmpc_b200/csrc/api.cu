@@ -142,6 +142,18 @@ int tfmpc_env_create(int kind, int n, int m, int nz, const double *p, int64_t np
 
   if (cudaGetDevice(&e->device) != cudaSuccess) { free(e); return tfmpc_set_error(TFMPC_E_CUDA, "no CUDA device: %s", cudaGetErrorString(cudaGetLastError())); }
 
+  if (e->small) {
+    real tab[QP_MAX_STEPS];
+    s.qp_klast = qp_step_table(tab);
+    if (cudaMalloc((void **)&e->dsteps, sizeof(tab)) != cudaSuccess || cudaMemcpy(e->dsteps, tab, sizeof(tab), cudaMemcpyHostToDevice) != cudaSuccess) {
+      int rc = tfmpc_set_error(TFMPC_E_CUDA, "box-QP step table upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+      if (e->dsteps) cudaFree(e->dsteps);
+      free(e);
+      return rc;
+    }
+    s.qp_steps = e->dsteps;
+  }
+
   if (kind == TFMPC_ENV_RESERVOIR || kind == TFMPC_ENV_HVAC || (kind == TFMPC_ENV_NAVLQR && !e->small)) {
     // device blob for the warp-per-problem kernels: vec[16][32] | matF[32][32] | matB[32][32], zero padded
     const int NV = 16;
@@ -204,6 +216,7 @@ int tfmpc_env_create(int kind, int n, int m, int nz, const double *p, int64_t np
 int tfmpc_env_destroy(tfmpc_env_t *e) {
   if (!e) return TFMPC_OK;
   if (e->dblob) cudaFree(e->dblob);
+  if (e->dsteps) cudaFree(e->dsteps);
   if (e->h_scratch) cudaFree(e->h_scratch);
   free(e);
   return TFMPC_OK;

@@ -40,11 +40,29 @@ HD real r_cos(real v) { return cosf(v); }
 // ---- environment parameters -------------------------------------------------------
 // Small environments (thread-per-problem kernels): passed by value as a kernel argument,
 // so every field is a constant-bank operand.
+#define QP_MAX_STEPS 128
 struct EnvSmall {
   int kind, n, m, nz, bounded;
   real goal[4], low[4], high[4], beta;
   real center[MAXZ][2], decay[MAXZ];
+  // box-QP backtracking step sizes (real)(0.6^k), k = 0..qp_klast, produced with the reference's own double
+  // recurrence `step *= 0.6` (utils/optimization.py:88); qp_klast is the first k with 0.6^k < 1e-22 (:93).
+  // Device (or, in the host emulation, host) pointer; used by the warp-cooperative backtracking.
+  const real *qp_steps;
+  int qp_klast;
 };
+
+// fills tab[0..QP_MAX_STEPS) and returns qp_klast
+inline int qp_step_table(real *tab) {
+  double step = 1.0;
+  int klast = -1;
+  for (int k = 0; k < QP_MAX_STEPS; k++) {
+    tab[k] = (real)step;
+    if (klast < 0 && step < 1e-22) klast = k;
+    step *= 0.6;
+  }
+  return klast;
+}
 
 // Large environments (warp-per-problem kernels): one device blob, one row per lane.
 // Reservoir rows: cap lb ub lowpen highpen sppen rain | D[n][n] | Dt[n][n]
@@ -69,6 +87,7 @@ struct tfmpc_env {
   EnvSmall es;
   EnvLarge el;
   real *dblob;       // device storage behind el
+  real *dsteps;      // device copy of the box-QP step table (es.qp_steps)
   int device;
   // cached device scratch for the *_host entry points
   void *h_scratch;

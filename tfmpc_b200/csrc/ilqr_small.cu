@@ -153,18 +153,27 @@ __global__ void __launch_bounds__(kThreads) k_init(EnvSmall e, int64_t B, int T,
   start_pass<KIND, N, M>(e, T, x, u_init + b * T * M, buf_traj<N, M>(w, 0, b), none);
 }
 
-template <int KIND, int N, int M>
+// COOP: warp-cooperative box-QP backtracking (bounded environments).  The loop is warp-uniform: lanes past the end of
+// the active list shadow the last active problem (same nominal, gains written to the spare slot S-1, no state written),
+// so that all 32 lanes stay in lock step through the cooperative phases.
+template <int KIND, int N, int M, bool COOP>
 __global__ void __launch_bounds__(kThreads) k_tick_backward(EnvSmall e, IlqrOpts o, int T, WS w, int parity) {
   const int cnt = w.count[parity];
   if (blockIdx.x == 0 && threadIdx.x == 0) w.count[parity ^ 1] = 0;  // filled by this tick's line-search kernel
   const int *__restrict__ list = w.list[parity];
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
-    const int64_t b = list[i];
+  const int lane = threadIdx.x & 31;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  for (int base = tid - lane; base < cnt; base += nth) {
+    const int i = base + lane;
+    const bool valid = i < cnt;
+    const int64_t b = list[valid ? i : cnt - 1];
     Prob p;
     load_prob(w, b, p);
-    tick_backward<KIND, N, M>(e, o, T, buf_traj<N, M>(w, p.cur, b), buf_gain<N, M>(w, b), p);
-    w.n_bwd[b] = p.n_bwd; w.status[b] = p.status; w.phase[b] = p.phase;
-    w.J_hat[b] = p.J_hat; w.dV1[b] = p.dV1; w.dV2[b] = p.dV2;
+    tick_backward<KIND, N, M, COOP>(e, o, T, buf_traj<N, M>(w, p.cur, b), buf_gain<N, M>(w, valid ? b : w.S - 1), p);
+    if (valid) {
+      w.n_bwd[b] = p.n_bwd; w.status[b] = p.status; w.phase[b] = p.phase;
+      w.J_hat[b] = p.J_hat; w.dV1[b] = p.dV1; w.dV2[b] = p.dV2;
+    }
   }
 }
 
@@ -362,7 +371,7 @@ int small_ilqr_forward(const tfmpc_env *e, int64_t B, int T, const real *states,
   return TFMPC_OK;
 }
 
-static int64_t padded_slots(int64_t B) { return (B + 31) / 32 * 32; }
+static int64_t padded_slots(int64_t B) { return (B + 1 + 31) / 32 * 32; }  // >= B + 1: slot S-1 is a spare (see k_tick_backward)
 
 int64_t small_ilqr_workspace_bytes(const tfmpc_env *e, int64_t B, int T) { return ws_bytes_for(padded_slots(B), T, e->n, e->m); }
 
@@ -414,7 +423,8 @@ static int solve_launch(const tfmpc_env *e, int64_t B, int T, const real *x0, co
   const int ticks = o.max_iterations + kExtraTicks;
   const int head = std::min(ticks, kHeadTicks);
   for (int t = 0; t < head; t++) {
-    k_tick_backward<KIND, N, M><<<g_bwd, kThreads, 0, s>>>(e->es, o, T, w, t & 1);
+    if (e->bounded) k_tick_backward<KIND, N, M, true><<<g_bwd, kThreads, 0, s>>>(e->es, o, T, w, t & 1);
+    else k_tick_backward<KIND, N, M, false><<<g_bwd, kThreads, 0, s>>>(e->es, o, T, w, t & 1);
     k_tick_linesearch<KIND, N, M><<<g_ls, kThreads, 0, s>>>(e->es, o, T, w, t & 1);
   }
   cudaStream_t ts = (ticks > head) ? tail_stream(e->device) : nullptr;
@@ -430,7 +440,8 @@ static int solve_launch(const tfmpc_env *e, int64_t B, int T, const real *x0, co
   cudaStream_t q = ts ? ts : s;
   if (ts) { cudaEventRecord(fork, s); cudaStreamWaitEvent(ts, fork, 0); }
   for (int t = head; t < ticks; t++) {
-    k_tick_backward<KIND, N, M><<<g_bwd_t, kThreads, 0, q>>>(e->es, o, T, w, t & 1);
+    if (e->bounded) k_tick_backward<KIND, N, M, true><<<g_bwd_t, kThreads, 0, q>>>(e->es, o, T, w, t & 1);
+    else k_tick_backward<KIND, N, M, false><<<g_bwd_t, kThreads, 0, q>>>(e->es, o, T, w, t & 1);
     k_tick_linesearch<KIND, N, M><<<g_ls_t, kThreads, 0, q>>>(e->es, o, T, w, t & 1);
   }
   k_costs<KIND, N, M><<<gB, kThreads, 0, q>>>(e->es, B, T, w, stats);

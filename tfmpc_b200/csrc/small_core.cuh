@@ -269,6 +269,149 @@ HD int boxqp(const real *H, const real *q, const real *lo, const real *hi, real 
   return status;
 }
 
+#ifdef __CUDACC__
+// Warp-synchronous projected-Newton box-QP: the same algorithm and the same arithmetic as boxqp() above, executed by
+// all 32 lanes of a warp TOGETHER, one problem per lane (`active` = this lane has a QP to solve).
+//
+// Why: in the thread-per-problem backward pass ~7% of the Armijo searches need more than one trial step and ~2% of
+// them backtrack for tens of steps; with one problem per lane the whole warp waits for its slowest lane, and ncu showed
+// more than half of all warp instructions of the backward kernel issued inside that loop with ~2 of 32 lanes active.
+// Here every lane tries the full step (k = 0) on its own problem; the lanes that must backtrack are then served one at
+// a time by the WHOLE warp: the owner broadcasts its problem (shuffles), lane j evaluates trial step k0 + j, and a
+// ballot finds the first step the sequential loop would have stopped at.  Results are bit-identical to boxqp():
+// each trial evaluates exactly the expressions of the sequential iteration k, with the same step size (real)(0.6^k).
+template <int M>
+__device__ __forceinline__ int boxqp_warp(bool active, const real *steps, int klast, const real *H, const real *q, const real *lo,
+                                          const real *hi, real *x, real *L, bool *fr) {
+  constexpr unsigned FULL = 0xffffffffu;
+  const real rtol = (real)1e-8, armijo = (real)0.1, eps = (real)1e-6;
+  const int lane = threadIdx.x & 31;
+  bool clamped[M];
+  real g[M], search[M], xc[M];
+#pragma unroll
+  for (int i = 0; i < M; i++) { clamped[i] = false; fr[i] = true; xc[i] = x[i]; }
+  real value = active ? qp_value<M>(H, q, x) : (real)0, old_value = 0;
+  int status = 0;
+  bool act = active;
+  for (int it = 0; it < 100; it++) {
+    if (!__any_sync(FULL, act)) break;
+    real sdotg = 0, vc = value;
+    bool need = false;
+    if (act && it > 0 && (old_value - value) < rtol * r_abs(old_value)) act = false;  // :27
+    if (act) {
+      old_value = value;
+      bool changed = false, allc = true;
+#pragma unroll
+      for (int i = 0; i < M; i++) {
+        real s = 0;
+#pragma unroll
+        for (int j = 0; j < M; j++) s += H[i * M + j] * x[j];
+        g[i] = q[i] + s;  // :34
+      }
+#pragma unroll
+      for (int i = 0; i < M; i++) {  // :121-127
+        bool c = (r_abs(x[i] - lo[i]) < eps && g[i] > 0) || (r_abs(hi[i] - x[i]) < eps && g[i] < 0);
+        changed = changed || (c != clamped[i]);
+        clamped[i] = c;
+        fr[i] = !c;
+        allc = allc && c;
+      }
+      if (it == 0 || changed) {  // :37-51
+        if (chol_masked<M>(H, fr, L)) { status = 2; act = false; }
+      }
+      if (act && allc) act = false;  // :53
+      if (act) {
+        real gn = 0;
+#pragma unroll
+        for (int i = 0; i < M; i++) gn += fr[i] ? g[i] * g[i] : (real)0;
+        if (r_sqrt(gn) < eps) act = false;  // :58-62
+      }
+      if (act) {
+        real rhs[M];
+#pragma unroll
+        for (int i = 0; i < M; i++) {  // grad_clamped = q + H (x * clamped), :65
+          real s = 0;
+#pragma unroll
+          for (int j = 0; j < M; j++) s += H[i * M + j] * (clamped[j] ? x[j] : (real)0);
+          rhs[i] = fr[i] ? q[i] + s : (real)0;
+        }
+        chol_solve<M>(L, rhs);
+#pragma unroll
+        for (int i = 0; i < M; i++) {
+          search[i] = fr[i] ? -rhs[i] - x[i] : (real)0;  // :70
+          sdotg += search[i] * g[i];
+        }
+        if (sdotg >= 0) act = false;  // :75-79
+      }
+      if (act) {  // trial step k = 0 (step = 1), :82-85
+        bool moved = false;
+#pragma unroll
+        for (int i = 0; i < M; i++) { xc[i] = r_clip(x[i] + (real)1 * search[i], lo[i], hi[i]); moved = moved || (xc[i] != x[i]); }
+        if (!moved) vc = old_value;  // degenerate, see boxqp()
+        else {
+          vc = qp_value<M>(H, q, xc);
+          need = (vc - old_value) / ((real)1 * sdotg) < armijo;
+        }
+      }
+    }
+    // cooperative backtracking for the lanes whose full step failed the Armijo test
+    unsigned nm = __ballot_sync(FULL, need);
+    while (nm) {
+      const int src = __ffs(nm) - 1;
+      nm &= nm - 1;
+      real bH[M * M], bq[M], bx[M], bs[M], blo[M], bhi[M];
+#pragma unroll
+      for (int i = 0; i < M * M; i++) bH[i] = __shfl_sync(FULL, H[i], src);
+#pragma unroll
+      for (int i = 0; i < M; i++) {
+        bq[i] = __shfl_sync(FULL, q[i], src); bx[i] = __shfl_sync(FULL, x[i], src); bs[i] = __shfl_sync(FULL, search[i], src);
+        blo[i] = __shfl_sync(FULL, lo[i], src); bhi[i] = __shfl_sync(FULL, hi[i], src);
+      }
+      const real bold = __shfl_sync(FULL, old_value, src), bsd = __shfl_sync(FULL, sdotg, src);
+      for (int k0 = 1; k0 <= klast; k0 += 32) {
+        const int k = k0 + lane;
+        const bool vk = k <= klast;
+        const real st = steps[vk ? k : klast];
+        real cxc[M];
+        bool moved = false;
+#pragma unroll
+        for (int i = 0; i < M; i++) { cxc[i] = r_clip(bx[i] + st * bs[i], blo[i], bhi[i]); moved = moved || (cxc[i] != bx[i]); }
+        const real cvc = qp_value<M>(bH, bq, cxc);
+        const bool cond = (cvc - bold) / (st * bsd) < armijo;
+        // the sequential loop stops at k if the trial did not move (degenerate), passed the test, or was the last one (:93-95)
+        const unsigned tm = __ballot_sync(FULL, vk && (!moved || !cond || k == klast));
+        if (tm) {
+          const int f = __ffs(tm) - 1;
+          const bool f_moved = __shfl_sync(FULL, moved, f);
+          const real f_vc = __shfl_sync(FULL, cvc, f);
+          real f_xc[M];
+#pragma unroll
+          for (int i = 0; i < M; i++) f_xc[i] = __shfl_sync(FULL, cxc[i], f);
+          if (lane == src) {
+            if (!f_moved) {
+#pragma unroll
+              for (int i = 0; i < M; i++) xc[i] = x[i];
+              vc = old_value;
+            } else {
+#pragma unroll
+              for (int i = 0; i < M; i++) xc[i] = f_xc[i];
+              vc = f_vc;
+            }
+          }
+          break;
+        }
+      }
+    }
+    if (act) {
+#pragma unroll
+      for (int i = 0; i < M; i++) x[i] = xc[i];
+      value = vc;
+    }
+  }
+  return status;
+}
+#endif  // __CUDACC__
+
 // ------------------------------------------------------------------ iLQR backward, one timestep
 // Structural zeros of the analytic linearisation, known at compile time per environment.  Skipping a
 // product with a structural zero (or the addition of one) is exact, so the result equals the dense
@@ -282,7 +425,8 @@ struct Traits {
 
 // tfmpc/solvers/ilqr.py:108-170 with the controllers of :357-387.  V_x, V_xx, J, dV1, dV2 are
 // carried across timesteps.  Returns 0, 1 (unconstrained Cholesky failed) or 2 (box-QP failed).
-template <int KIND, int N, int M>
+// COOP = true: called by all 32 lanes of a warp in lock step (device only); the box-QP then runs warp-cooperatively.
+template <int KIND, int N, int M, bool COOP = false>
 HD int backward_step(const EnvSmall &e, const Lin<N, M> &L, const real *u, real mu, real *V_x, real *V_xx, real &J, real &dV1,
                      real &dV2, real *K, real *k) {
   typedef Traits<KIND> TR;
@@ -378,12 +522,23 @@ HD int backward_step(const EnvSmall &e, const Lin<N, M> &L, const real *u, real 
     bool any_nz = false;
 #pragma unroll
     for (int i = 0; i < N * N; i++) any_nz = any_nz || (V_xx[i] != 0);
-    if (any_nz) {  // :137-138 -> _get_constrained_controller :364-387
-      real lo[M], hi[M], Lf[M * M];
-      bool fr[M];
+    bool enter_qp = any_nz;
+#ifdef __CUDA_ARCH__
+    if (COOP) enter_qp = __any_sync(0xffffffffu, any_nz);  // warp-uniform: every lane enters, lanes without a QP idle inside
+#endif
+    real lo[M], hi[M], Lf[M * M];
+    bool fr[M];
+    int st = 0;
+    if (enter_qp) {  // :137-138 -> _get_constrained_controller :364-387
 #pragma unroll
       for (int i = 0; i < M; i++) { lo[i] = e.low[i] - u[i]; hi[i] = e.high[i] - u[i]; k[i] = (lo[i] + hi[i]) / (real)2; }
-      int st = boxqp<M>(Q_uu_reg, Q_u, lo, hi, k, Lf, fr);
+#ifdef __CUDA_ARCH__
+      if (COOP) st = boxqp_warp<M>(any_nz, e.qp_steps, e.qp_klast, Q_uu_reg, Q_u, lo, hi, k, Lf, fr);
+      else
+#endif
+        st = boxqp<M>(Q_uu_reg, Q_u, lo, hi, k, Lf, fr);
+    }
+    if (any_nz) {
       if (st) status = 2;
 #pragma unroll
       for (int j = 0; j < N; j++) {  // K[free] = -cholesky_solve(Hfree, Q_ux_reg[free]); clamped rows 0
@@ -617,7 +772,7 @@ struct CostSink {
 
 // iLQR.backward over the whole horizon (ilqr.py:94-172), linearisation fused (ilqr.py:84-92).
 // Also accumulates sum_t max_i |k|/(|u|+1) for the g_norm test of ilqr.py:243.
-template <int KIND, int N, int M, class TJ, class GN>
+template <int KIND, int N, int M, bool COOP = false, class TJ, class GN>
 HD int backward_pass(const EnvSmall &e, int T, const TJ &nom, real mu, const GN &gain, real &J, real &dV1, real &dV2, real &gsum) {
   real V_x[N], V_xx[N * N], x[N], u[M];
   nom.load_x(T, x);
@@ -635,8 +790,8 @@ HD int backward_pass(const EnvSmall &e, int T, const TJ &nom, real mu, const GN 
     Lin<N, M> L;
     env_linearize<KIND, N, M>(e, x, u, L);
     real K[M * N], k[M];
-    int st = backward_step<KIND, N, M>(e, L, u, mu, V_x, V_xx, J, dV1, dV2, K, k);
-    if (st == 1) return 1;
+    int st = backward_step<KIND, N, M, COOP>(e, L, u, mu, V_x, V_xx, J, dV1, dV2, K, k);
+    if (st == 1 && !COOP) return 1;  // (COOP is used for bounded envs only: the unconstrained failure cannot occur)
     if (st) status = st;
     real mx = 0;
 #pragma unroll
@@ -650,47 +805,58 @@ HD int backward_pass(const EnvSmall &e, int T, const TJ &nom, real mu, const GN 
   return status;
 }
 
-// iLQR.forward (ilqr.py:174-212).  The nominal records and gains are loaded TWO steps ahead of their use
-// (explicit software prefetch, a 2-deep register ring): one step of arithmetic is shorter than a DRAM / far-L2
-// round trip, and in the line search this loop is otherwise bound by exactly that latency.
+// iLQR.forward (ilqr.py:174-212).
+template <int N, int M>
+struct NomRec { real xh[N], uh[M], K[M * N], k[M]; };  // nominal state/action and gains of one timestep
+
+template <int KIND, int N, int M, class TO>
+HD void forward_step(const EnvSmall &e, real alpha, const NomRec<N, M> &r, int t, real *x, const TO &out, const CostSink &Co, real &J,
+                     real &residual) {
+  real u[M], xn[N];
+#pragma unroll
+  for (int i = 0; i < M; i++) {
+    real s = 0;
+#pragma unroll
+    for (int j = 0; j < N; j++) s += r.K[i * N + j] * (x[j] - r.xh[j]);
+    real du = alpha * r.k[i] + s;                             // :194
+    u[i] = r_clip(r.uh[i] + du, e.low[i], e.high[i]);         // :196-197
+    residual = r_max(residual, r_abs(du));                    // :206 (pre-clip)
+  }
+  real c = env_cost<KIND, N, M>(e, x, u);
+  env_step<KIND, N, M>(e, x, u, xn);
+  out.store_xu(t, x, u);
+  Co.put(t, c);
+  J += c;
+#pragma unroll
+  for (int i = 0; i < N; i++) x[i] = xn[i];
+}
+
+// The records are loaded TWO steps ahead of their use through a 3-slot register ring; the loop is unrolled by 3 so
+// that the ring needs no register-to-register rotation (a rotating MOV would wait on the load it copies from and
+// collapse the prefetch distance to one step -- seen as 73% of the stall samples of the line-search kernel in ncu).
+// One step of arithmetic is shorter than a DRAM / far-L2 round trip, hence the distance of two.
 template <int KIND, int N, int M, class TJ, class GN, class TO>
 HD void forward_pass(const EnvSmall &e, int T, const TJ &nom, const GN &gain, real alpha, const TO &out, const CostSink &Co, real &J,
                      real &residual) {
-  real x[N], u[M], xn[N];
-  real xh[N], uh[M], Kt[M * N], kt[M];        // step t
-  real xh1[N], uh1[M], K1[M * N], k1[M];      // step t+1
+  real x[N];
+  NomRec<N, M> r0, r1, r2;
   J = 0; residual = 0;
-  nom.load_xu(0, xh, uh);
-  gain.load(0, Kt, kt);
-  nom.load_xu(T > 1 ? 1 : 0, xh1, uh1);
-  gain.load(T > 1 ? 1 : 0, K1, k1);
+  const int last = T - 1;
+  nom.load_xu(0, r0.xh, r0.uh); gain.load(0, r0.K, r0.k);
+  nom.load_xu(1 < last ? 1 : last, r1.xh, r1.uh); gain.load(1 < last ? 1 : last, r1.K, r1.k);
 #pragma unroll
-  for (int i = 0; i < N; i++) x[i] = xh[i];
-  for (int t = 0; t < T; t++) {
-    real xh2[N], uh2[M], K2[M * N], k2[M];    // step t+2, in flight while steps t and t+1 compute
-    const int t2 = (t + 2 < T) ? t + 2 : T - 1;  // the last steps re-read the final record (harmless) instead of branching
-    nom.load_xu(t2, xh2, uh2);
-    gain.load(t2, K2, k2);
-#pragma unroll
-    for (int i = 0; i < M; i++) {
-      real s = 0;
-#pragma unroll
-      for (int j = 0; j < N; j++) s += Kt[i * N + j] * (x[j] - xh[j]);
-      real du = alpha * kt[i] + s;                            // :194
-      u[i] = r_clip(uh[i] + du, e.low[i], e.high[i]);         // :196-197
-      residual = r_max(residual, r_abs(du));                  // :206 (pre-clip)
+  for (int i = 0; i < N; i++) x[i] = r0.xh[i];
+  for (int t = 0; t < T; t += 3) {
+    { const int tl = t + 2 < last ? t + 2 : last; nom.load_xu(tl, r2.xh, r2.uh); gain.load(tl, r2.K, r2.k); }
+    forward_step<KIND, N, M>(e, alpha, r0, t, x, out, Co, J, residual);
+    if (t + 1 < T) {
+      { const int tl = t + 3 < last ? t + 3 : last; nom.load_xu(tl, r0.xh, r0.uh); gain.load(tl, r0.K, r0.k); }
+      forward_step<KIND, N, M>(e, alpha, r1, t + 1, x, out, Co, J, residual);
     }
-    real c = env_cost<KIND, N, M>(e, x, u);
-    env_step<KIND, N, M>(e, x, u, xn);
-    out.store_xu(t, x, u);
-    Co.put(t, c);
-    J += c;
-#pragma unroll
-    for (int i = 0; i < N; i++) { x[i] = xn[i]; xh[i] = xh1[i]; xh1[i] = xh2[i]; }
-#pragma unroll
-    for (int i = 0; i < M; i++) { uh[i] = uh1[i]; kt[i] = k1[i]; uh1[i] = uh2[i]; k1[i] = k2[i]; }
-#pragma unroll
-    for (int i = 0; i < M * N; i++) { Kt[i] = K1[i]; K1[i] = K2[i]; }
+    if (t + 2 < T) {
+      { const int tl = t + 4 < last ? t + 4 : last; nom.load_xu(tl, r1.xh, r1.uh); gain.load(tl, r1.K, r1.k); }
+      forward_step<KIND, N, M>(e, alpha, r2, t + 2, x, out, Co, J, residual);
+    }
   }
   out.store_x(T, x);
   real cf = env_final_cost<KIND, N, M>(e, x);
@@ -737,13 +903,13 @@ HD void prob_init(Prob &p) {
 }
 
 // _backward (:285-315) + the g_norm test (:243-248).  Leaves p.phase = PH_SEARCH if a line search must follow.
-template <int KIND, int N, int M, class TJ, class GN>
+template <int KIND, int N, int M, bool COOP = false, class TJ, class GN>
 HD void tick_backward(const EnvSmall &e, const IlqrOpts &o, int T, const TJ &nom, const GN &gain, Prob &p) {
   real gsum;
   double mu_l = p.mu, delta_l = p.delta;  // the retry bump is local, ilqr.py:308-309,315
   int bst, tries = 0;
   for (;;) {
-    bst = backward_pass<KIND, N, M>(e, T, nom, (real)mu_l, gain, p.J_hat, p.dV1, p.dV2, gsum);
+    bst = backward_pass<KIND, N, M, COOP>(e, T, nom, (real)mu_l, gain, p.J_hat, p.dV1, p.dV2, gsum);
     p.n_bwd++;
     if (bst != 1 || ++tries > 200) break;
     delta_l = fmax(o.delta_0, delta_l * o.delta_0);

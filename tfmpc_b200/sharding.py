@@ -1,0 +1,59 @@
+"""Sharding of a problem batch over the GPUs of one node.
+
+Problems are independent, so the batch is cut into contiguous blocks, one per rank; nothing is exchanged while
+solving, and the per-problem summaries (total cost, iteration count, status) are all-gathered once at the end
+over whatever backend the process group uses (NCCL on GPUs, gloo in the CPU tests).
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_range(batch, rank, world):
+    """Contiguous [lo, hi) block of `batch` problems for `rank` of `world`; sizes differ by at most one."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError(f"bad rank/world {rank}/{world}")
+    base, extra = divmod(int(batch), world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def shard(tensor, rank, world):
+    lo, hi = shard_range(tensor.shape[0], rank, world)
+    return tensor[lo:hi]
+
+
+def gather_summaries(total_cost, iterations, status, batch, group=None):
+    """All-gather per-problem summaries of ragged shards into full-batch tensors (every rank gets them).
+
+    total_cost [b_r] float, iterations [b_r] int32, status [b_r] int32 for this rank's shard of `batch`."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return total_cost, iterations, status
+    rank = dist.get_rank(group)
+    sizes = [shard_range(batch, r, world)[1] - shard_range(batch, r, world)[0] for r in range(world)]
+    assert total_cost.shape[0] == sizes[rank]
+    pad = max(sizes)
+
+    def padded(t):
+        out = torch.zeros(pad, dtype=t.dtype, device=t.device)
+        out[: t.shape[0]] = t
+        return out
+
+    outs = []
+    for t in (total_cost, iterations, status):
+        bufs = [torch.empty(pad, dtype=t.dtype, device=t.device) for _ in range(world)]
+        dist.all_gather(bufs, padded(t), group=group)
+        outs.append(torch.cat([b[:s] for b, s in zip(bufs, sizes)]))
+    return tuple(outs)
+
+
+def solve_sharded(solver, x0, T, u_init, group=None):
+    """iLQR solve of the global batch (x0 [B,n], u_init [B,T,m], identical on every rank): each rank solves its
+    block on its own GPU, then the summaries are gathered.  Returns (local result dict, (cost, iterations, status))."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    B = x0.shape[0]
+    lo, hi = shard_range(B, rank, world)
+    out = solver.solve_device(x0[lo:hi], T, u_init=u_init[lo:hi])
+    summary = gather_summaries(out["costs"].sum(1), out["stats"][:, 0].contiguous(), out["stats"][:, 3].contiguous(), B, group)
+    return out, summary

@@ -146,6 +146,32 @@ def cpu_baseline(name, T, sample, threads=0, repeats=1):
     return best[0] / best[1], cores, best[0], best[1]
 
 
+def reference_under_shim(name, T, problems=3):
+    """Extra data point for the CPU arm: the UNMODIFIED reference sources (baseline/_ref, installed with pip --no-deps)
+    executed under the torch-backed TensorFlow API shim (oracle/tf_shim), one process, a handful of problems.  This is the
+    reference's own Python control flow (py_function callback per timestep and all) with torch CPU kernels in place of
+    TensorFlow's; None when baseline/_ref is absent."""
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref, "tfmpc")):
+        return None
+    import tempfile
+    cfg = workload_cfg(name)
+    x0, u0 = make_inputs(cfg, problems, T, seed=12345)
+    with tempfile.TemporaryDirectory() as tmp:
+        json.dump(cfg, open(os.path.join(tmp, "env.json"), "w"))
+        np.savez(os.path.join(tmp, "in.npz"), x0=x0, u0=u0)
+        env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(ROOT, "oracle", "tf_shim"), ref]), OMP_NUM_THREADS="1")
+        try:
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "run_reference_shim.py"), os.path.join(tmp, "env.json"),
+                                os.path.join(tmp, "in.npz")], env=env, capture_output=True, text=True, timeout=600)
+            d = json.loads(r.stdout.strip().splitlines()[-1])
+        except Exception as exc:  # noqa: BLE001
+            return {"error": str(exc)[:200]}
+    return {"value_per_core": d["problem_iterations"] / d["seconds"], "unit": "problem-iterations/s", "cores": 1,
+            "kind": "reference sources under a torch-backed TensorFlow API shim", "sample": f"{d['problems']} problems, {d['seconds']:.1f} s",
+            "iterations": d["iterations"]}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -169,7 +195,9 @@ def run_reference(args):
                              "sample": f"{sample} problems of the workload per step, {args.steps} steps"},
             "e2e": {"value": value, "unit": "problem-iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    if args.workload == "c3":
+        line["reference_under_shim"] = reference_under_shim(args.workload, T)
+    print(json.dumps(line), flush=True)
 
 
 def run_ours(args):
@@ -354,7 +382,7 @@ def run_ours(args):
             line["cpu_baseline"] = {"value": v, "unit": "problem-iterations/s", "cores": cores, "kind": "port",
                                     "sample": f"{sample} problems of the same workload ({pi:.0f} problem-iterations in {dt:.1f} s), "
                                               "C/OpenMP restatement of the reference algorithm (oracle/), one problem per thread"}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

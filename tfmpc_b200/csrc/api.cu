@@ -1,4 +1,5 @@
 // extern "C" boundary of libtfmpc_b200 (see include/tfmpc_b200.h for the contract).
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdarg>
@@ -198,6 +199,12 @@ int tfmpc_env_create(int kind, int n, int m, int nz, const double *p, int64_t np
     } else {  // large NavigationLQR: goal, beta, low, high rows
       for (int i = 0; i < n; i++) { vec[0 * 32 + i] = (real)p[i]; vec[2 * 32 + i] = (real)e->low[i]; vec[3 * 32 + i] = (real)e->high[i]; }
       vec[1 * 32] = (real)p[n];
+    }
+    e->max_row_nnz = 0;
+    for (int i = 0; i < 32; i++) {
+      int cf = 0, cb = 0;
+      for (int j = 0; j < 32; j++) { cf += mF[i * 32 + j] != (real)0; cb += mB[i * 32 + j] != (real)0; }
+      e->max_row_nnz = std::max(e->max_row_nnz, std::max(cf, cb));
     }
     size_t bytes = h.size() * sizeof(real);
     if (cudaMalloc((void **)&e->dblob, bytes) != cudaSuccess || cudaMemcpy(e->dblob, h.data(), bytes, cudaMemcpyHostToDevice) != cudaSuccess) {

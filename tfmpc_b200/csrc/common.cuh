@@ -88,6 +88,7 @@ struct tfmpc_env {
   EnvLarge el;
   real *dblob;       // device storage behind el
   real *dsteps;      // device copy of the box-QP step table (es.qp_steps)
+  int max_row_nnz;   // large envs: max non-zeros per row over the forward and backward coupling matrices
   int device;
   // cached device scratch for the *_host entry points
   void *h_scratch;

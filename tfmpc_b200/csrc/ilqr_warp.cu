@@ -32,28 +32,72 @@ __device__ __forceinline__ real group_max(real v) {
   for (int o = G / 2; o > 0; o >>= 1) v = r_max(v, __shfl_xor_sync(FULL, v, o, G));
   return v;
 }
-// sum_j row[j] * v_j over the lanes of the group, j ascending (the reference's matmul order)
-template <int G>
-__device__ __forceinline__ real group_matvec(const real (&row)[G], real v) {
-  real acc = 0;
+// One row of a coupling matrix, held by the lane that owns that row.  NZ == 0: dense (G registers, G shuffles per
+// matvec).  NZ > 0: the row has at most NZ non-zeros (reservoir chains: 1, room grids: 4) and is kept as (column,
+// value) pairs in ascending column order -- NZ shuffles per matvec.  Skipping structural zeros is exact and the
+// remaining terms are accumulated in the same (ascending) order as the dense loop.
+template <int G, int NZ>
+struct Row {
+  real val[NZ > 0 ? NZ : G];
+  int col[NZ > 0 ? NZ : 1];
+
+  __device__ void load(const real *__restrict__ src) {  // src = 32 padded entries of this lane's row
+    if (NZ == 0) {
 #pragma unroll
-  for (int j = 0; j < G; j++) acc += row[j] * __shfl_sync(FULL, v, j, G);
-  return acc;
-}
+      for (int j = 0; j < G; j++) val[j] = src[j];
+    } else {
+      int c = 0;
+#pragma unroll
+      for (int q = 0; q < NZ; q++) { val[q] = 0; col[q] = 0; }
+      for (int j = 0; j < G; j++) {
+        real v = src[j];
+        if (v != (real)0 && c < NZ) {
+#pragma unroll
+          for (int q = 0; q < NZ; q++) if (q == c) { val[q] = v; col[q] = j; }
+          c++;
+        }
+      }
+    }
+  }
+  // sum_j row[j] * v_j
+  __device__ __forceinline__ real dot(real v) const {
+    real acc = 0;
+    if (NZ == 0) {
+#pragma unroll
+      for (int j = 0; j < G; j++) acc += val[j] * __shfl_sync(FULL, v, j, G);
+    } else {
+#pragma unroll
+      for (int q = 0; q < NZ; q++) acc += val[q] * __shfl_sync(FULL, v, col[q], G);
+    }
+    return acc;
+  }
+  // sum_j -row[j] * (x_i - x_j)
+  __device__ __forceinline__ real diffuse(real x) const {
+    real acc = 0;
+    if (NZ == 0) {
+#pragma unroll
+      for (int j = 0; j < G; j++) acc += -val[j] * (x - __shfl_sync(FULL, x, j, G));
+    } else {
+#pragma unroll
+      for (int q = 0; q < NZ; q++) acc += -val[q] * (x - __shfl_sync(FULL, x, col[q], G));
+    }
+    return acc;
+  }
+};
 
 // Per-lane environment: parameters of component i in registers.
-template <int KIND, int G>
+template <int KIND, int G, int NZ = 0>
 struct LaneEnv {
   real p[9];
-  real rowF[G], rowB[G];
+  Row<G, NZ> rowF, rowB;
   bool in_range;  // lane index < n
 
   __device__ void load(const EnvLarge &e, int i) {
     in_range = i < e.n;
 #pragma unroll
     for (int r = 0; r < 9; r++) p[r] = e.vec[r * 32 + i];
-#pragma unroll
-    for (int j = 0; j < G; j++) { rowF[j] = e.matF[i * 32 + j]; rowB[j] = e.matB[i * 32 + j]; }
+    rowF.load(e.matF + i * 32);
+    rowB.load(e.matB + i * 32);
   }
 
   // per-lane term of cost(state, action) / final_cost(state); the caller sums over the group
@@ -76,16 +120,14 @@ struct LaneEnv {
     real xn;
     if (KIND == TFMPC_ENV_RESERVOIR) {  // reservoir/__init__.py:47-62
       real out = u * x;
-      real inflow = group_matvec<G>(rowF, out);
+      real inflow = rowF.dot(out);
       real cap = act ? p[0] : (real)1;
       real vap = (real)0.5 * r_sin(x / cap) * x;
       xn = x + p[6] + inflow - vap - out;
     } else {  // hvac/__init__.py:69-91,128-149
       real air = u * p[3];
       real heating = air * (real)1.006 * ((real)40.0 - x);
-      real cbr = 0;
-#pragma unroll
-      for (int j = 0; j < G; j++) cbr += -rowF[j] * (x - __shfl_sync(FULL, x, j, G));
+      real cbr = rowF.diffuse(x);
       real cwo = p[4] * (p[6] - x);
       real cwh = p[5] * (p[7] - x);
       xn = x + p[2] * (heating + cbr + cwo + cwh);
@@ -107,7 +149,7 @@ struct LaneEnv {
 
   // Q_x = l_x + f_x^T V_x, Q_u = l_u + f_u^T V_x for this lane (ilqr.py:122-123), analytic f_x, f_u
   __device__ __forceinline__ void adjoint(bool act, real x, real u, real V, real lx, real &Q_x, real &Q_u) const {
-    real BV = group_matvec<G>(rowB, V);
+    real BV = rowB.dot(V);
     if (KIND == TFMPC_ENV_RESERVOIR) {  // f_x = I - diag(dvap) - diag(u) + D^T diag(u); f_u = -diag(x) + D^T diag(x)
       real cap = act ? p[0] : (real)1;
       real a = x / cap;
@@ -125,8 +167,8 @@ struct LaneEnv {
 
 // ---- one problem, one group --------------------------------------------------------
 // backward sweep (K == 0): writes k[t][i]; returns J, dV1 (dV2 == 0) and sum_t max_i |k|/(|u|+1)
-template <int KIND, int G>
-__device__ __forceinline__ void group_backward(const LaneEnv<KIND, G> &E, bool act, int n, int T, int i, const real *__restrict__ X,
+template <int KIND, int G, int NZ>
+__device__ __forceinline__ void group_backward(const LaneEnv<KIND, G, NZ> &E, bool act, int n, int T, int i, const real *__restrict__ X,
                                                const real *__restrict__ U, real *__restrict__ kout, real lo, real hi, real &J,
                                                real &dV1, real &gsum) {
   real xT = act ? X[(int64_t)T * n + i] : (real)0;
@@ -152,8 +194,8 @@ __device__ __forceinline__ void group_backward(const LaneEnv<KIND, G> &E, bool a
 }
 
 // forward rollout with K == 0 (ilqr.py:174-212): u = clip(u_hat + alpha k)
-template <int KIND, int G, bool WRITE_C>
-__device__ __forceinline__ void group_forward(const LaneEnv<KIND, G> &E, bool act, int n, int T, int i, const real *__restrict__ Xh,
+template <int KIND, int G, int NZ, bool WRITE_C>
+__device__ __forceinline__ void group_forward(const LaneEnv<KIND, G, NZ> &E, bool act, int n, int T, int i, const real *__restrict__ Xh,
                                               const real *__restrict__ Uh, const real *__restrict__ kin, real alpha, real lo, real hi,
                                               real *__restrict__ Xo, real *__restrict__ Uo, real *__restrict__ Co, real &J, real &residual) {
   real x = act ? Xh[i] : (real)0;
@@ -179,8 +221,8 @@ __device__ __forceinline__ void group_forward(const LaneEnv<KIND, G> &E, bool ac
   residual = group_max<G>(res);
 }
 
-template <int KIND, int G, bool WRITE_C>
-__device__ __forceinline__ void group_start(const LaneEnv<KIND, G> &E, bool act, int n, int T, int i, const real *__restrict__ x0,
+template <int KIND, int G, int NZ, bool WRITE_C>
+__device__ __forceinline__ void group_start(const LaneEnv<KIND, G, NZ> &E, bool act, int n, int T, int i, const real *__restrict__ x0,
                                             const real *__restrict__ Ui, real *__restrict__ Xo, real *__restrict__ Uo, real *__restrict__ Co) {
   real x = act ? x0[i] : (real)0;
   if (act) Xo[i] = x;
@@ -195,12 +237,12 @@ __device__ __forceinline__ void group_start(const LaneEnv<KIND, G> &E, bool act,
 }
 
 // ---- stage kernels (one group per problem, grid-stride) -----------------------------------
-template <int KIND, int G>
+template <int KIND, int G, int NZ>
 __global__ void __launch_bounds__(32 * kWarpsPerBlock) kw_start(EnvLarge e, int64_t B, int T, const real *__restrict__ x0,
                                                                 const real *__restrict__ u_init, real *__restrict__ states,
                                                                 real *__restrict__ actions, real *__restrict__ costs) {
   const int i = threadIdx.x % G, n = e.n;
-  LaneEnv<KIND, G> E;
+  LaneEnv<KIND, G, NZ> E;
   E.load(e, i);
   int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G, ngroups = (int64_t)gridDim.x * blockDim.x / G;
   // whole warps iterate together so that the group shuffles stay convergent
@@ -210,17 +252,17 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) kw_start(EnvLarge e, int6
     bool valid = b < B;
     int64_t bb = valid ? b : B - 1;
     real *Xo = states + bb * (T + 1) * n, *Uo = actions + bb * T * n, *Co = costs + bb * (T + 1);
-    group_start<KIND, G, true>(E, E.in_range && valid, n, T, i, x0 + bb * n, u_init + bb * T * n, Xo, Uo, Co);
+    group_start<KIND, G, NZ, true>(E, E.in_range && valid, n, T, i, x0 + bb * n, u_init + bb * T * n, Xo, Uo, Co);
   }
 }
 
-template <int KIND, int G>
+template <int KIND, int G, int NZ>
 __global__ void __launch_bounds__(32 * kWarpsPerBlock) kw_backward(EnvLarge e, int64_t B, int T, const real *__restrict__ states,
                                                                    const real *__restrict__ actions, real *__restrict__ K,
                                                                    real *__restrict__ k, real *__restrict__ J, real *__restrict__ dV1,
                                                                    real *__restrict__ dV2, int32_t *__restrict__ status, real lo, real hi) {
   const int i = threadIdx.x % G, n = e.n;
-  LaneEnv<KIND, G> E;
+  LaneEnv<KIND, G, NZ> E;
   E.load(e, i);
   int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G, ngroups = (int64_t)gridDim.x * blockDim.x / G;
   int64_t warp_first = gid - (threadIdx.x % 32) / G;
@@ -230,7 +272,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) kw_backward(EnvLarge e, i
     int64_t bb = valid ? b : B - 1;
     const bool act = E.in_range && valid;
     real Jb, d1, g;
-    group_backward<KIND, G>(E, act, n, T, i, states + bb * (T + 1) * n, actions + bb * T * n, k + bb * T * n, lo, hi, Jb, d1, g);
+    group_backward<KIND, G, NZ>(E, act, n, T, i, states + bb * (T + 1) * n, actions + bb * T * n, k + bb * T * n, lo, hi, Jb, d1, g);
     if (act) {
       for (int t = 0; t < T; t++)
         for (int j = 0; j < n; j++) K[((bb * T + t) * n + i) * n + j] = 0;
@@ -239,13 +281,13 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) kw_backward(EnvLarge e, i
   }
 }
 
-template <int KIND, int G>
+template <int KIND, int G, int NZ>
 __global__ void __launch_bounds__(32 * kWarpsPerBlock) kw_forward(EnvLarge e, int64_t B, int T, const real *__restrict__ states,
                                                                   const real *__restrict__ actions, const real *__restrict__ k, real alpha,
                                                                   real *__restrict__ xs, real *__restrict__ us, real *__restrict__ cs,
                                                                   real *__restrict__ J, real *__restrict__ residual, real lo, real hi) {
   const int i = threadIdx.x % G, n = e.n;
-  LaneEnv<KIND, G> E;
+  LaneEnv<KIND, G, NZ> E;
   E.load(e, i);
   int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G, ngroups = (int64_t)gridDim.x * blockDim.x / G;
   int64_t warp_first = gid - (threadIdx.x % 32) / G;
@@ -254,7 +296,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) kw_forward(EnvLarge e, in
     bool valid = b < B;
     int64_t bb = valid ? b : B - 1;
     real Jb, res;
-    group_forward<KIND, G, true>(E, E.in_range && valid, n, T, i, states + bb * (T + 1) * n, actions + bb * T * n, k + bb * T * n, alpha,
+    group_forward<KIND, G, NZ, true>(E, E.in_range && valid, n, T, i, states + bb * (T + 1) * n, actions + bb * T * n, k + bb * T * n, alpha,
                                  lo, hi, xs + bb * (T + 1) * n, us + bb * T * n, cs + bb * (T + 1), Jb, res);
     if (valid && i == 0) { J[b] = Jb; residual[b] = res; }
   }
@@ -265,7 +307,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) kw_forward(EnvLarge e, in
 // iLQR.solve for them: schedule, convergence tests and first-accept line search on the device.
 // When a warp holds several problems (G < 32) their control flow is made warp-uniform by
 // iterating until every group in the warp is done (finished groups idle with active = false).
-template <int KIND, int G>
+template <int KIND, int G, int NZ>
 __global__ void __launch_bounds__(32 * kWarpsPerBlock) kw_solve(EnvLarge e, IlqrOpts o, int64_t B, int T, const real *__restrict__ x0,
                                                                 const real *__restrict__ u_init, real *__restrict__ states,
                                                                 real *__restrict__ actions, real *__restrict__ costs,
@@ -273,7 +315,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) kw_solve(EnvLarge e, Ilqr
                                                                 real *__restrict__ ws, real lo, real hi) {
   constexpr int PPW = 32 / G;  // problems per warp
   const int lane = threadIdx.x % 32, i = lane % G, sub = lane / G, n = e.n;
-  LaneEnv<KIND, G> E;
+  LaneEnv<KIND, G, NZ> E;
   E.load(e, i);
   const int64_t per = (int64_t)(3 * T + 1) * n;  // workspace reals per problem: cand X, cand U, k
   for (;;) {
@@ -289,7 +331,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) kw_solve(EnvLarge e, Ilqr
     real *Xb[2] = {states + bb * (T + 1) * n, ws + bb * per};
     real *Ub[2] = {actions + bb * T * n, ws + bb * per + (int64_t)(T + 1) * n};
     real *kb = ws + bb * per + (int64_t)(2 * T + 1) * n;
-    group_start<KIND, G, false>(E, live, n, T, i, x0 + bb * n, u_init + bb * T * n, Xb[0], Ub[0], nullptr);
+    group_start<KIND, G, NZ, false>(E, live, n, T, i, x0 + bb * n, u_init + bb * T * n, Xb[0], Ub[0], nullptr);
     double mu = 0.0, delta = 1.0;  // kept for fidelity with ilqr.py:215-216,261-270; mu is inert when V_xx == 0
     int cur = 0, n_bwd = 0, n_fwd = 0, status = TFMPC_ST_MAXITER, iteration = 0;
     bool done = !valid;
@@ -301,7 +343,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) kw_solve(EnvLarge e, Ilqr
       bool iter_open = !done;  // this group still has to finish outer iteration `it`
       while (__any_sync(FULL, iter_open)) {
         real J_hat, dV1, g;
-        group_backward<KIND, G>(E, live && iter_open, n, T, i, Xb[cur], Ub[cur], kb, lo, hi, J_hat, dV1, g);
+        group_backward<KIND, G, NZ>(E, live && iter_open, n, T, i, Xb[cur], Ub[cur], kb, lo, hi, J_hat, dV1, g);
         if (iter_open) n_bwd++;
         g = g / (real)T;  // ilqr.py:243
         bool stop = false;
@@ -315,7 +357,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) kw_solve(EnvLarge e, Ilqr
         for (int ai = 0; ai < N_ALPHA; ai++) {  // :322 first-accept backtracking
           if (!__any_sync(FULL, searching)) break;
           real alpha = o.alphas[ai], J, res;
-          group_forward<KIND, G, false>(E, live && searching, n, T, i, Xb[cur], Ub[cur], kb, alpha, lo, hi, Xb[cur ^ 1], Ub[cur ^ 1],
+          group_forward<KIND, G, NZ, false>(E, live && searching, n, T, i, Xb[cur], Ub[cur], kb, alpha, lo, hi, Xb[cur ^ 1], Ub[cur ^ 1],
                                         nullptr, J, res);
           if (searching) {
             n_fwd++;
@@ -381,15 +423,20 @@ int sm_count(int device) {
 
 }  // namespace
 
-#define WARP_DISPATCH(e, CALL)                                           \
+#define WARP_DISPATCH_G(e, KD, NZ, CALL)                                \
   do {                                                                   \
     int g_ = pick_group((e)->n);                                         \
+    if (g_ == 4) { CALL(KD, 4, NZ); } else if (g_ == 8) { CALL(KD, 8, NZ); } \
+    else if (g_ == 16) { CALL(KD, 16, NZ); } else { CALL(KD, 32, NZ); }  \
+  } while (0)
+// sparse rows (<= 4 non-zeros per row of both coupling matrices: reservoir chains, room grids) or dense rows
+#define WARP_DISPATCH(e, CALL)                                           \
+  do {                                                                   \
+    const bool sp_ = (e)->max_row_nnz <= 4;                              \
     if ((e)->kind == TFMPC_ENV_RESERVOIR) {                              \
-      if (g_ == 4) { CALL(TFMPC_ENV_RESERVOIR, 4); } else if (g_ == 8) { CALL(TFMPC_ENV_RESERVOIR, 8); } \
-      else if (g_ == 16) { CALL(TFMPC_ENV_RESERVOIR, 16); } else { CALL(TFMPC_ENV_RESERVOIR, 32); }      \
+      if (sp_) WARP_DISPATCH_G(e, TFMPC_ENV_RESERVOIR, 4, CALL); else WARP_DISPATCH_G(e, TFMPC_ENV_RESERVOIR, 0, CALL); \
     } else {                                                             \
-      if (g_ == 4) { CALL(TFMPC_ENV_HVAC, 4); } else if (g_ == 8) { CALL(TFMPC_ENV_HVAC, 8); }           \
-      else if (g_ == 16) { CALL(TFMPC_ENV_HVAC, 16); } else { CALL(TFMPC_ENV_HVAC, 32); }                \
+      if (sp_) WARP_DISPATCH_G(e, TFMPC_ENV_HVAC, 4, CALL); else WARP_DISPATCH_G(e, TFMPC_ENV_HVAC, 0, CALL); \
     }                                                                    \
   } while (0)
 
@@ -405,7 +452,7 @@ int warp_ilqr_start(const tfmpc_env *e, int64_t B, int T, const real *x0, const 
                     cudaStream_t s) {
   int rc = check_large(e);
   if (rc) return rc;
-#define CALL(K, G) kw_start<K, G><<<stage_grid(e, B), 32 * kWarpsPerBlock, 0, s>>>(e->el, B, T, x0, u_init, states, actions, costs)
+#define CALL(K, G, NZ) kw_start<K, G, NZ><<<stage_grid(e, B), 32 * kWarpsPerBlock, 0, s>>>(e->el, B, T, x0, u_init, states, actions, costs)
   WARP_DISPATCH(e, CALL);
 #undef CALL
   LAUNCH_CHECK();
@@ -418,7 +465,7 @@ int warp_ilqr_backward(const tfmpc_env *e, int64_t B, int T, const real *states,
   if (rc) return rc;
   (void)mu;  // inert: V_xx == 0 for these environments (see the header comment)
   real lo = (real)e->low[0], hi = (real)e->high[0];
-#define CALL(KD, G) kw_backward<KD, G><<<stage_grid(e, B), 32 * kWarpsPerBlock, 0, s>>>(e->el, B, T, states, actions, K, k, J, dV1, dV2, status, lo, hi)
+#define CALL(KD, G, NZ) kw_backward<KD, G, NZ><<<stage_grid(e, B), 32 * kWarpsPerBlock, 0, s>>>(e->el, B, T, states, actions, K, k, J, dV1, dV2, status, lo, hi)
   WARP_DISPATCH(e, CALL);
 #undef CALL
   LAUNCH_CHECK();
@@ -431,7 +478,7 @@ int warp_ilqr_forward(const tfmpc_env *e, int64_t B, int T, const real *states, 
   if (rc) return rc;
   (void)K;  // K == 0 for these environments
   real lo = (real)e->low[0], hi = (real)e->high[0];
-#define CALL(KD, G) kw_forward<KD, G><<<stage_grid(e, B), 32 * kWarpsPerBlock, 0, s>>>(e->el, B, T, states, actions, k, (real)alpha, xs, us, cs, J, residual, lo, hi)
+#define CALL(KD, G, NZ) kw_forward<KD, G, NZ><<<stage_grid(e, B), 32 * kWarpsPerBlock, 0, s>>>(e->el, B, T, states, actions, k, (real)alpha, xs, us, cs, J, residual, lo, hi)
   WARP_DISPATCH(e, CALL);
 #undef CALL
   LAUNCH_CHECK();
@@ -456,7 +503,7 @@ int warp_ilqr_solve(const tfmpc_env *e, int64_t B, int T, const real *x0, const 
   int64_t blocks_needed = (warps_needed + kWarpsPerBlock - 1) / kWarpsPerBlock;
   int64_t resident = (int64_t)sm_count(e->device) * 4;  // persistent: 4 blocks x 4 warps per SM
   unsigned grid = (unsigned)(blocks_needed < resident ? blocks_needed : resident);
-#define CALL(KD, G) kw_solve<KD, G><<<grid, 32 * kWarpsPerBlock, 0, s>>>(e->el, o, B, T, x0, u_init, states, actions, costs, stats, counter, wsr, lo, hi)
+#define CALL(KD, G, NZ) kw_solve<KD, G, NZ><<<grid, 32 * kWarpsPerBlock, 0, s>>>(e->el, o, B, T, x0, u_init, states, actions, costs, stats, counter, wsr, lo, hi)
   WARP_DISPATCH(e, CALL);
 #undef CALL
   LAUNCH_CHECK();

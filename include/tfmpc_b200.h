@@ -179,6 +179,18 @@ int tfmpc_ilqr_start(const tfmpc_env_t *env, int64_t B, int T, const tfmpc_real 
 int tfmpc_ilqr_backward(const tfmpc_env_t *env, int64_t B, int T, const tfmpc_real *states, const tfmpc_real *actions,
                         double mu, tfmpc_real *K, tfmpc_real *k, tfmpc_real *J, tfmpc_real *dV1, tfmpc_real *dV2,
                         int32_t *status, void *stream);
+/* iLQR.backward exactly as the reference defines it (ilqr.py:94-172): consumes caller-supplied derivative models
+ * (TransitionApprox / CostApprox / FinalCostApprox, diffenv.py:6-8) for B problems and any n, m <= 32:
+ * f_x [B,T,n,n] f_u [B,T,n,m] l [B,T] l_x [B,T,n] l_u [B,T,m] l_xx [B,T,n,n] l_uu [B,T,m,m] l_xu [B,T,n,m],
+ * fl [B] fl_x [B,n] fl_xx [B,n,n], actions [B,T,m]; low/high [m] are HOST arrays (+-inf = unbounded,
+ * env.action_space.low/high).  All three controllers (:357-387) with the dispatch rule of :136-143.
+ * -> K [B,T,m,n], k [B,T,m], J/dV1/dV2 [B], status [B] (0, 1 = Cholesky of Q_uu_reg failed, 2 = box-QP failed).
+ * One warp per problem; each timestep's block is staged into shared memory with TMA bulk copies. */
+int tfmpc_ilqr_backward_staged(int64_t B, int T, int n, int m, const double *low, const double *high, const tfmpc_real *actions,
+                               const tfmpc_real *f_x, const tfmpc_real *f_u, const tfmpc_real *l, const tfmpc_real *l_x,
+                               const tfmpc_real *l_u, const tfmpc_real *l_xx, const tfmpc_real *l_uu, const tfmpc_real *l_xu,
+                               const tfmpc_real *fl, const tfmpc_real *fl_x, const tfmpc_real *fl_xx, double mu, tfmpc_real *K,
+                               tfmpc_real *k, tfmpc_real *J, tfmpc_real *dV1, tfmpc_real *dV2, int32_t *status, void *stream);
 /* iLQR.forward (ilqr.py:174-212) -> xs [B,T+1,n], us [B,T,m], cs [B,T+1], J [B], residual [B] */
 int tfmpc_ilqr_forward(const tfmpc_env_t *env, int64_t B, int T, const tfmpc_real *states, const tfmpc_real *actions,
                        const tfmpc_real *K, const tfmpc_real *k, double alpha, tfmpc_real *xs, tfmpc_real *us,

@@ -589,3 +589,78 @@ def test_lqr_dump_load_roundtrip(tmp_path):
         assert torch.equal(getattr(lq, k), getattr(lq2, k))
     x0 = np.array([[-1.0], [0.5], [3.6]])
     assert np.allclose(lq.solve(x0, 10).states, lq2.solve(x0, 10).states)
+
+
+# ------------------------------------------------------------------ generic dense staged backward (reference signature)
+@pytest.mark.parametrize("case", ["nav", "navlqr2_free", "navlqr2_box", "navlqr8_free", "navlqr8_box", "navlqr5_box", "res4", "hvac6",
+                                  "res20", "hvac32", "navlqr32_box"])
+def test_backward_staged_dense_vs_oracle(prec, orc, case):
+    """tfmpc_ilqr_backward_staged (warp per problem, TMA-staged derivative blocks, Cholesky / box-QP / bang-bang controllers)
+    against the oracle's dense backward pass on the same models, for every environment kind and n up to 32."""
+    from tfmpc_b200 import ops
+    from tfmpc_b200.envs import synthetic
+    rng = np.random.RandomState(7)
+    goal = lambda n: list(rng.uniform(-5, 5, size=n))  # noqa: E731
+    cfg, B, T = {
+        "nav": (synthetic.navigation_config(), 16, 20),
+        "navlqr2_free": (synthetic.navlqr_config([5.5, -9.0], 0.5), 8, 10),
+        "navlqr2_box": (synthetic.navlqr_config([5.5, -9.0], 5.0, -1.0, 1.0), 8, 10),
+        "navlqr8_free": (synthetic.navlqr_config(goal(8), 0.7), 6, 8),
+        "navlqr8_box": (synthetic.navlqr_config(goal(8), 0.7, -0.5, 0.8), 6, 8),
+        "navlqr5_box": (synthetic.navlqr_config(goal(5), 1.3, -0.5, 0.8), 6, 8),       # n % 4 != 0: cooperative-load path
+        "res4": (synthetic.reservoir_config(4), 8, 12),
+        "hvac6": (synthetic.hvac_grid_config(2, 3), 8, 12),
+        "res20": (synthetic.reservoir_config(20), 4, 10),
+        "hvac32": (synthetic.hvac_grid_config(4, 8), 4, 10),
+        "navlqr32_box": (synthetic.navlqr_config(goal(32), 0.4, -0.3, 0.3), 3, 6),
+    }[case]
+    x0, u0 = _batch_case(cfg, B, T, 3)
+    oenv = orc.make_env(cfg)
+    n, m = oenv.n, oenv.m
+    xs, us, cs = orc.ilqr_start(oenv, x0, u0)
+    lin = orc.env_linearize(oenv, xs[:, :-1].reshape(B * T, n), us.reshape(B * T, m))
+    fin = orc.env_linearize(oenv, xs[:, -1], np.zeros((B, m)))
+    r = lambda a, *s: _cu(a.reshape(B, T, *s), prec)  # noqa: E731
+    tm = (None, r(lin["f_x"], n, n), r(lin["f_u"], n, m))
+    cm = (r(lin["l"]), r(lin["l_x"], n), r(lin["l_u"], m), r(lin["l_xx"], n, n), r(lin["l_uu"], m, m), None, r(lin["l_xu"], n, m))
+    fm = (_cu(fin["fl"], prec), _cu(fin["fl_x"], prec), _cu(fin["fl_xx"], prec))
+    c = cfg["config"]
+    if cfg["cls_name"] == "Navigation":
+        lo, hi = np.ravel(c["low"]), np.ravel(c["high"])
+    elif cfg["cls_name"] == "NavigationLQR":
+        lo = np.full(n, -np.inf if c.get("low") is None else c["low"]); hi = np.full(n, np.inf if c.get("high") is None else c["high"])
+    else:
+        lo, hi = np.zeros(n), np.ones(n)
+    for mu in (0.0, 1e-3, 1.0):
+        out = ops.ilqr_backward_staged(_cu(us, prec), tm, cm, fm, lo, hi, mu)
+        ref = orc.ilqr_backward(oenv, xs, us, mu)
+        assert (_np(out["status"]) == ref["status"]).all()
+        t = tol(prec, 2e-3, 1e-9)
+        kd = np.abs(_np(out["k"]) - ref["k"])
+        if cfg["cls_name"] == "Reservoir":      # exact ties of the bang-bang rule (see tests/test_oracle_golden.py)
+            flips = kd > 1e-3
+            assert np.all(np.abs(kd[flips] - 1.0) < 1e-4) and flips.mean() < 0.2
+            continue
+        scale = max(1.0, np.abs(ref["k"]).max())
+        assert kd.max() < t * scale, (case, mu, kd.max())
+        assert np.abs(_np(out["K"]) - ref["K"]).max() < t * max(1.0, np.abs(ref["K"]).max()), (case, mu)
+        for key in ("J", "dV1", "dV2"):
+            assert np.all(np.abs(_np(out[key]) - ref[key]) <= t * np.maximum(1.0, np.abs(ref[key]))), (case, mu, key)
+
+
+def test_backward_reference_signature_uses_the_models(prec):
+    """iLQR.backward(T, actions, transition_model, cost_model, final_cost_model, mu) consumes the models it is given
+    (reference ilqr.py:94): scaling l_u changes k exactly as the algebra says, which a re-linearising kernel could not see."""
+    from tfmpc_b200.envs import synthetic
+    from tfmpc_b200.solvers.ilqr import iLQR
+    env = _env(synthetic.navlqr_config([5.5, -9.0], 2.0), prec)
+    solver = iLQR(env, dtype=_dt(prec))
+    x, u, c = solver.start(np.zeros((2, 1)), 6, seed=1)
+    tm, cm, fm = solver.derivatives(x, u)
+    K1, k1, J1, d1, d2 = solver.backward(6, u, tm, cm, fm, mu=0.0)
+    K2, k2, *_ = solver.backward(6, u, states=x, mu=0.0)
+    assert np.allclose(_np(K1), _np(K2), atol=tol(prec, 1e-4, 1e-10)) and np.allclose(_np(k1), _np(k2), atol=tol(prec, 1e-3, 1e-9))
+    cm2 = cm._replace(l_u=cm.l_u + 1.0)          # a model the environment itself would never produce
+    K3, k3, *_ = solver.backward(6, u, tm, cm2, fm, mu=0.0)
+    assert np.allclose(_np(K3), _np(K1), atol=tol(prec, 1e-4, 1e-10))
+    assert np.abs(_np(k3) - _np(k1)).max() > 1e-2

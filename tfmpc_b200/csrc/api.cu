@@ -291,6 +291,20 @@ int tfmpc_ilqr_forward(const tfmpc_env_t *e, int64_t B, int T, const real *state
                       : warp_ilqr_forward(e, B, T, states, actions, K, k, alpha, xs, us, cs, J, residual, (cudaStream_t)stream);
 }
 
+int tfmpc_ilqr_backward_staged(int64_t B, int T, int n, int m, const double *low, const double *high, const real *actions, const real *f_x,
+                               const real *f_u, const real *l, const real *l_x, const real *l_u, const real *l_xx, const real *l_uu,
+                               const real *l_xu, const real *fl, const real *fl_x, const real *fl_xx, double mu, real *K, real *k, real *J,
+                               real *dV1, real *dV2, int32_t *status, void *stream) {
+  REQ(low && high && actions && f_x && f_u && l && l_x && l_u && l_xx && l_uu && l_xu && fl && fl_x && fl_xx && K && k && J && dV1 && dV2,
+      "tfmpc_ilqr_backward_staged: null argument");
+  REQ(B >= 0 && T >= 1 && n >= 1 && m >= 1 && n <= MAXD && m <= MAXD, "tfmpc_ilqr_backward_staged: size out of range");
+  if (B == 0) return TFMPC_OK;
+  int bounded = 1;  // gym Box.is_bounded(): every bound finite (ilqr.py:136)
+  for (int i = 0; i < m; i++) if (std::isinf(low[i]) || std::isinf(high[i])) bounded = 0;
+  return dense_backward_launch(B, T, n, m, bounded, low, high, actions, f_x, f_u, l, l_x, l_u, l_xx, l_uu, l_xu, fl, fl_x, fl_xx, mu, K, k, J, dV1,
+                               dV2, status, (cudaStream_t)stream);
+}
+
 int64_t tfmpc_ilqr_workspace_bytes(const tfmpc_env_t *e, int64_t B, int T) {
   if (!e || B < 0 || T < 1) return tfmpc_set_error(TFMPC_E_INVALID, "tfmpc_ilqr_workspace_bytes: bad argument");
   int64_t b = use_small(e) ? small_ilqr_workspace_bytes(e, B, T) : warp_ilqr_workspace_bytes(e, B, T);

@@ -147,3 +147,7 @@ int lqr_forward_launch(int64_t B, int n, int m, int T, const real *F, int64_t sF
                        cudaStream_t s);
 int lqr_step_launch(int64_t R, int n, int m, const real *F, int64_t sF, const real *f, int64_t sf, const real *C, int64_t sC, const real *c,
                     int64_t sc, const real *x, const real *u, real *xn, real *cost, real *fcost, cudaStream_t s);
+int dense_backward_launch(int64_t B, int T, int n, int m, int bounded, const double *low, const double *high, const real *actions,
+                          const real *f_x, const real *f_u, const real *l, const real *l_x, const real *l_u, const real *l_xx,
+                          const real *l_uu, const real *l_xu, const real *fl, const real *fl_x, const real *fl_xx, double mu, real *K,
+                          real *k, real *J, real *dV1, real *dV2, int32_t *status, cudaStream_t s);

@@ -178,6 +178,31 @@ def ilqr_backward(env, states, actions, mu=1.0):
     return dict(K=K, k=k, J=J, dV1=dV1, dV2=dV2, status=status)
 
 
+def ilqr_backward_staged(actions, tm, cm, fm, low, high, mu=1.0):
+    """iLQR.backward from explicit derivative models (the reference's signature, ilqr.py:94): generic dense kernel, any
+    n, m <= 32.  actions [B,T,m]; tm = (f, f_x [B,T,n,n], f_u [B,T,n,m]); cm = (l [B,T], l_x [B,T,n], l_u [B,T,m], l_xx, l_uu,
+    l_ux, l_xu [B,T,n,m]); fm = (l [B], l_x [B,n], l_xx [B,n,n]); low/high: action bounds (length m, +-inf = unbounded)."""
+    import numpy as np
+    N.require_cuda()
+    actions = _c(actions)
+    B, T, m = actions.shape
+    f_x, f_u = _c(tm[1]), _c(tm[2])
+    n = f_x.shape[-1]
+    l, l_x, l_u, l_xx, l_uu, l_xu = _c(cm[0]), _c(cm[1].reshape(B, T, n)), _c(cm[2].reshape(B, T, m)), _c(cm[3]), _c(cm[4]), _c(cm[6])
+    fl, fl_x, fl_xx = _c(fm[0].reshape(B)), _c(fm[1].reshape(B, n)), _c(fm[2])
+    lib = N.load(_prec(actions))
+    lo = (C.c_double * m)(*[float(v) for v in np.asarray(low, dtype=np.float64).reshape(-1)])
+    hi = (C.c_double * m)(*[float(v) for v in np.asarray(high, dtype=np.float64).reshape(-1)])
+    K, k = _empty(actions, B, T, m, n), _empty(actions, B, T, m)
+    J, dV1, dV2 = _empty(actions, B), _empty(actions, B), _empty(actions, B)
+    status = torch.empty(B, dtype=torch.int32, device=actions.device)
+    ins = [N.dev_ptr(lib, t) for t in (actions, f_x, f_u, l, l_x, l_u, l_xx, l_uu, l_xu, fl, fl_x, fl_xx)]
+    outs = [N.dev_ptr(lib, t) for t in (K, k, J, dV1, dV2)] + [N.dev_ptr(lib, status, True)]
+    N.check(lib, lib.tfmpc_ilqr_backward_staged(C.c_int64(B), T, n, m, lo, hi, *[p.p for p in ins], C.c_double(float(mu)),
+                                                *[p.p for p in outs], N.stream_ptr()))
+    return dict(K=K, k=k, J=J, dV1=dV1, dV2=dV2, status=status)
+
+
 def ilqr_forward(env, states, actions, K, k, alpha=1.0):
     states, actions, K, k = _c(states), _c(actions), _c(K), _c(k)
     B, T = actions.shape[0], actions.shape[1]

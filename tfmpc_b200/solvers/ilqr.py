@@ -123,25 +123,29 @@ class iLQR:
             tm = TransitionApprox(*[a[0] for a in tm])
             cm = CostApprox(*[a[0] for a in cm])
             fm = FinalCostApprox(*[a[0] for a in fm])
-        self._last_nominal = _Nominal(xs, us)
         return tm, cm, fm
 
     def backward(self, T, actions, transition_model=None, cost_model=None, final_cost_model=None, mu=1.0, states=None):
         """ilqr.py:94-172 -> (K [T,m,n], k [T,m,1], J, dV1, dV2).
 
-        The CUDA backward pass fuses the linearisation (derivatives are recomputed analytically in
-        registers along the nominal trajectory instead of being staged through HBM), so it needs the
-        nominal STATES as well as the actions: pass `states=`, or call `derivatives(states, actions)`
-        first (as the reference's solve and tests do) and the states given there are used."""
+        With the reference's full signature (derivative models given) the generic dense kernel consumes exactly those
+        models (tfmpc_ilqr_backward_staged: one warp per problem, TMA-staged blocks, all three controllers).  Called
+        with `states=` instead of models, the environment-specialised kernel re-linearises analytically in registers
+        (the path solve() uses)."""
         us, single = self._traj(actions, self.env.action_size)
-        if states is None:
-            last = getattr(self, "_last_nominal", None)
-            if last is None or last.actions.shape != us.shape:
-                raise N.TfmpcError("iLQR.backward needs the nominal states: pass states= or call derivatives() first")
-            xs = last.states
+        if transition_model is not None and cost_model is not None and final_cost_model is not None:
+            B, T_ = us.shape[0], us.shape[1]
+            dev = lambda a: torch.as_tensor(a).to(device=us.device, dtype=self.dtype)  # noqa: E731
+            lift = (lambda a: dev(a).unsqueeze(0)) if single else dev
+            tm = [lift(a) for a in transition_model]
+            cm = [lift(a) for a in cost_model]
+            fm = [lift(a) for a in final_cost_model]
+            out = ops.ilqr_backward_staged(us, tm, cm, fm, self.env.action_space.low, self.env.action_space.high, float(mu))
         else:
+            if states is None:
+                raise N.TfmpcError("iLQR.backward needs the derivative models (reference signature) or states=")
             xs, _ = self._traj(states, self.env.state_size)
-        out = ops.ilqr_backward(self._native(), xs, us, float(mu))
+            out = ops.ilqr_backward(self._native(), xs, us, float(mu))
         K, k = out["K"], out["k"].unsqueeze(-1)
         if single:
             return K[0], k[0], out["J"][0], out["dV1"][0], out["dV2"][0]

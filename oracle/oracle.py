@@ -43,13 +43,15 @@ def pack_env(cfg):
         n = goal.size
         low = c.get("low")
         high = c.get("high")
-        low = np.full(n, -np.inf if low is None else float(low))
-        high = np.full(n, np.inf if high is None else float(high))
+        # gym.spaces.Box stores its bounds as float32 (reference lqr/navigation/__init__.py:21), whatever the solver precision
+        low = np.full(n, -np.inf if low is None else float(np.float32(low)))
+        high = np.full(n, np.inf if high is None else float(np.float32(high)))
         return kind, n, n, 0, np.concatenate([goal, [float(c["beta"])], low, high])
     if kind == 1:
         centers = np.asarray(c["deceleration"]["center"], dtype=np.float64).reshape(-1, 2)
         decay = col(c["deceleration"]["decay"])
-        return kind, 2, 2, len(decay), np.concatenate([col(c["goal"]), col(c["low"]), col(c["high"]), centers.reshape(-1), decay])
+        f32 = lambda v: col(v).astype(np.float32).astype(np.float64)  # noqa: E731  (Box bounds are float32, navigation/__init__.py:21-24)
+        return kind, 2, 2, len(decay), np.concatenate([col(c["goal"]), f32(c["low"]), f32(c["high"]), centers.reshape(-1), decay])
     if kind == 2:
         keys = ["max_res_cap", "lower_bound", "upper_bound", "low_penalty", "high_penalty", "set_point_penalty",
                 "rain_shape", "rain_scale"]

@@ -628,7 +628,8 @@ def test_backward_staged_dense_vs_oracle(prec, orc, case):
     if cfg["cls_name"] == "Navigation":
         lo, hi = np.ravel(c["low"]), np.ravel(c["high"])
     elif cfg["cls_name"] == "NavigationLQR":
-        lo = np.full(n, -np.inf if c.get("low") is None else c["low"]); hi = np.full(n, np.inf if c.get("high") is None else c["high"])
+        # gym Box bounds are float32 (reference lqr/navigation/__init__.py:21)
+        lo = np.full(n, -np.inf if c.get("low") is None else np.float32(c["low"])); hi = np.full(n, np.inf if c.get("high") is None else np.float32(c["high"]))
     else:
         lo, hi = np.zeros(n), np.ones(n)
     for mu in (0.0, 1e-3, 1.0):
@@ -664,3 +665,48 @@ def test_backward_reference_signature_uses_the_models(prec):
     K3, k3, *_ = solver.backward(6, u, tm, cm2, fm, mu=0.0)
     assert np.allclose(_np(K3), _np(K1), atol=tol(prec, 1e-4, 1e-10))
     assert np.abs(_np(k3) - _np(k1)).max() > 1e-2
+
+
+@pytest.mark.parametrize("case", ["navlqr8_box", "navlqr8_free", "navlqr20_box", "navlqr32_box"])
+def test_ilqr_solve_dense_navlqr_vs_oracle(prec, orc, case):
+    """NavigationLQR with n > 4 goes through the generic dense path (warp per problem: k_solve_dense_navlqr).  It is a
+    linear-quadratic problem, so fp32 and fp64 agree on the iteration counts; cost within 1e-4 (fp32) / 1e-9 (fp64)."""
+    from tfmpc_b200.envs import synthetic
+    rng = np.random.RandomState(5)
+    n = int(case[6:].split("_")[0])
+    goal = list(rng.uniform(-4, 4, size=n))
+    cfg = synthetic.navlqr_config(goal, 0.8, -0.5, 0.7) if case.endswith("box") else synthetic.navlqr_config(goal, 0.8)
+    B, T = (24 if n <= 8 else 8), 10
+    g, r = _solve_both(cfg, prec, orc, B, T, seed=9)
+    a = _agreement(g["stats"][:, 0], g["costs"].sum(1), r["iterations"], r["costs"].sum(1))
+    assert (g["stats"][:, 3] == r["status"]).all()
+    assert a["same"] >= tol(prec, 0.9, 1.0), (a["same"], g["stats"][:, 0], r["iterations"])
+    same = a["d"] == 0
+    assert np.all(a["relc"][same] <= tol(prec, 1e-4, 1e-9))
+    assert np.max(np.abs(g["actions"] - r["actions"])[same]) < tol(prec, 5e-3, 1e-7)
+    if case.endswith("free"):
+        assert (g["stats"][:, 0] == 1).all()        # unconstrained LQ problem: 2 outer iterations (SURVEY 8(c))
+
+
+def test_stage_api_large_navlqr(prec, orc):
+    """start / derivatives / backward / forward for NavigationLQR n = 8 (dense path), reference signatures."""
+    from tfmpc_b200.envs import synthetic
+    from tfmpc_b200.solvers.ilqr import iLQR
+    rng = np.random.RandomState(2)
+    cfg = synthetic.navlqr_config(list(rng.uniform(-3, 3, size=8)), 1.5, -0.6, 0.6)
+    env = _env(cfg, prec)
+    solver = iLQR(env, dtype=_dt(prec))
+    oenv = orc.make_env(cfg)
+    x0, u0 = _batch_case(cfg, 1, 7, 1)
+    x, u, c = solver.start(x0[0].reshape(8, 1), 7, u_init=u0[0])
+    xs, us, cs = orc.ilqr_start(oenv, x0, u0)
+    t = tol(prec, 1e-5, 1e-12)
+    assert rel(_np(x)[..., 0], xs[0]) < t and rel(_np(c), cs[0]) < t
+    tm, cm, fm = solver.derivatives(x, u)
+    assert tuple(tm.f_x.shape) == (7, 8, 8) and tuple(cm.l_uu.shape) == (7, 8, 8)
+    K, k, J, dV1, dV2 = solver.backward(7, u, tm, cm, fm, mu=0.0)
+    ref = orc.ilqr_backward(oenv, xs, us, 0.0)
+    assert np.abs(_np(k)[..., 0] - ref["k"][0]).max() < tol(prec, 1e-4, 1e-10) and np.abs(_np(K) - ref["K"][0]).max() < tol(prec, 1e-4, 1e-10)
+    xs2, us2, cs2, J2, res2 = solver.forward(x, u, K, k, 0.5)
+    rf = orc.ilqr_forward(oenv, xs, us, ref["K"], ref["k"], 0.5)
+    assert rel(_np(xs2)[..., 0], rf["states"][0]) < tol(prec, 1e-4, 1e-10) and abs(float(J2) - rf["J"][0]) < tol(prec, 1e-4, 1e-10) * abs(rf["J"][0])

@@ -124,6 +124,8 @@ int tfmpc_env_create(int kind, int n, int m, int nz, const double *p, int64_t np
   s.kind = kind; s.n = n; s.m = m; s.nz = nz;
   if (kind == TFMPC_ENV_NAVLQR) {
     for (int i = 0; i < m; i++) { e->low[i] = p[n + 1 + i]; e->high[i] = p[n + 1 + m + i]; }
+    for (int i = 0; i < n; i++) e->goal[i] = p[i];
+    e->beta = p[n];
     e->small = n <= 4;
     if (e->small) {
       for (int i = 0; i < n; i++) { s.goal[i] = (real)p[i]; s.low[i] = (real)e->low[i]; s.high[i] = (real)e->high[i]; }
@@ -273,6 +275,8 @@ int tfmpc_boxqp(int64_t B, int m, const real *H, const real *q, const real *low,
 int tfmpc_ilqr_start(const tfmpc_env_t *e, int64_t B, int T, const real *x0, const real *u_init, real *states, real *actions, real *costs, void *stream) {
   REQ(e && x0 && u_init && states && actions && costs && B >= 0 && T >= 1, "tfmpc_ilqr_start: bad argument");
   if (B == 0) return TFMPC_OK;
+  if (!use_small(e) && e->kind == TFMPC_ENV_NAVLQR)
+    return dense_navlqr_forward(e, B, T, x0, nullptr, u_init, nullptr, nullptr, 0.0, states, actions, costs, nullptr, nullptr, (cudaStream_t)stream);
   return use_small(e) ? small_ilqr_start(e, B, T, x0, u_init, states, actions, costs, (cudaStream_t)stream)
                       : warp_ilqr_start(e, B, T, x0, u_init, states, actions, costs, (cudaStream_t)stream);
 }
@@ -287,6 +291,8 @@ int tfmpc_ilqr_forward(const tfmpc_env_t *e, int64_t B, int T, const real *state
                        real *xs, real *us, real *cs, real *J, real *residual, void *stream) {
   REQ(e && states && actions && K && k && xs && us && cs && J && residual && B >= 0 && T >= 1, "tfmpc_ilqr_forward: bad argument");
   if (B == 0) return TFMPC_OK;
+  if (!use_small(e) && e->kind == TFMPC_ENV_NAVLQR)
+    return dense_navlqr_forward(e, B, T, nullptr, states, actions, K, k, alpha, xs, us, cs, J, residual, (cudaStream_t)stream);
   return use_small(e) ? small_ilqr_forward(e, B, T, states, actions, K, k, alpha, xs, us, cs, J, residual, (cudaStream_t)stream)
                       : warp_ilqr_forward(e, B, T, states, actions, K, k, alpha, xs, us, cs, J, residual, (cudaStream_t)stream);
 }
@@ -307,7 +313,8 @@ int tfmpc_ilqr_backward_staged(int64_t B, int T, int n, int m, const double *low
 
 int64_t tfmpc_ilqr_workspace_bytes(const tfmpc_env_t *e, int64_t B, int T) {
   if (!e || B < 0 || T < 1) return tfmpc_set_error(TFMPC_E_INVALID, "tfmpc_ilqr_workspace_bytes: bad argument");
-  int64_t b = use_small(e) ? small_ilqr_workspace_bytes(e, B, T) : warp_ilqr_workspace_bytes(e, B, T);
+  int64_t b = use_small(e) ? small_ilqr_workspace_bytes(e, B, T)
+                           : (e->kind == TFMPC_ENV_NAVLQR ? dense_navlqr_workspace_bytes(e, B, T) : warp_ilqr_workspace_bytes(e, B, T));
   return (b + 255) / 256 * 256;
 }
 
@@ -319,6 +326,8 @@ int tfmpc_ilqr_solve(const tfmpc_env_t *e, int64_t B, int T, const real *x0, con
   IlqrOpts o;
   int rc = make_opts(opts, &o);
   if (rc) return rc;
+  if (!use_small(e) && e->kind == TFMPC_ENV_NAVLQR)
+    return dense_navlqr_solve(e, B, T, x0, u_init, o, states, actions, costs, stats, ws, ws_bytes, (cudaStream_t)stream);
   return use_small(e) ? small_ilqr_solve(e, B, T, x0, u_init, o, states, actions, costs, stats, ws, ws_bytes, (cudaStream_t)stream)
                       : warp_ilqr_solve(e, B, T, x0, u_init, o, states, actions, costs, stats, ws, ws_bytes, (cudaStream_t)stream);
 }

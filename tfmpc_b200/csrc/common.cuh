@@ -88,6 +88,7 @@ struct tfmpc_env {
   EnvLarge el;
   real *dblob;       // device storage behind el
   real *dsteps;      // device copy of the box-QP step table (es.qp_steps)
+  double goal[MAXD], beta;  // NavigationLQR (host copy; the dense path takes them as kernel arguments)
   int max_row_nnz;   // large envs: max non-zeros per row over the forward and backward coupling matrices
   int device;
   // cached device scratch for the *_host entry points
@@ -151,3 +152,8 @@ int dense_backward_launch(int64_t B, int T, int n, int m, int bounded, const dou
                           const real *f_x, const real *f_u, const real *l, const real *l_x, const real *l_u, const real *l_xx,
                           const real *l_uu, const real *l_xu, const real *fl, const real *fl_x, const real *fl_xx, double mu, real *K,
                           real *k, real *J, real *dV1, real *dV2, int32_t *status, cudaStream_t s);
+int64_t dense_navlqr_workspace_bytes(const tfmpc_env *e, int64_t B, int T);
+int dense_navlqr_solve(const tfmpc_env *e, int64_t B, int T, const real *x0, const real *u_init, const IlqrOpts &o, real *states,
+                       real *actions, real *costs, int32_t *stats, void *ws, int64_t ws_bytes, cudaStream_t s);
+int dense_navlqr_forward(const tfmpc_env *e, int64_t B, int T, const real *x0, const real *xh, const real *uh, const real *K, const real *k,
+                         double alpha, real *xs, real *us, real *cs, real *J, real *residual, cudaStream_t s);

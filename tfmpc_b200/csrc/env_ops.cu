@@ -109,7 +109,13 @@ struct LargeLane {  // parameters of component j of a Reservoir / HVAC env
   real p[9];
 };
 
+// large NavigationLQR (n > 4): vec rows = goal, beta (lane 0), low, high
 __device__ __forceinline__ real large_cost_term(int kind, const real *p, real x, real u, bool final) {
+  if (kind == TFMPC_ENV_NAVLQR) {
+    const real beta = __shfl_sync(FULL, p[1], 0);
+    const real c1 = (x - p[0]) * (x - p[0]);
+    return final ? c1 : c1 + beta * (u * u);   // per-lane share of c1 + beta c2 (lqr/navigation/__init__.py:34-41)
+  }
   if (kind == TFMPC_ENV_RESERVOIR) {
     real c1 = -p[3] * r_max((real)0, p[1] - x);
     real c2 = -p[4] * r_max((real)0, x - p[2]);
@@ -122,6 +128,7 @@ __device__ __forceinline__ real large_cost_term(int kind, const real *p, real x,
 }
 
 __device__ __forceinline__ real large_l_x(int kind, const real *p, real x) {
+  if (kind == TFMPC_ENV_NAVLQR) return (real)2 * (x - p[0]);
   if (kind == TFMPC_ENV_RESERVOIR) {
     real mid = (p[1] + p[2]) / (real)2.0;
     return p[3] * (real)(p[1] - x > 0) - p[4] * (real)(x - p[2] > 0) + p[5] * r_sgn(mid - x);
@@ -144,7 +151,9 @@ __global__ void __launch_bounds__(kThreads) kl_step(EnvLarge e, int64_t R, const
     real uv = (act && u) ? u[r * n + lane] : (real)0;
     if (xn) {
       real o;
-      if (e.kind == TFMPC_ENV_RESERVOIR) {
+      if (e.kind == TFMPC_ENV_NAVLQR) {
+        o = xv + uv;
+      } else if (e.kind == TFMPC_ENV_RESERVOIR) {
         real out = uv * xv, inflow = 0;
         for (int j = 0; j < n; j++) inflow += e.matF[lane * 32 + j] * __shfl_sync(FULL, out, j);
         real cap = act ? p[0] : (real)1;
@@ -161,11 +170,13 @@ __global__ void __launch_bounds__(kThreads) kl_step(EnvLarge e, int64_t R, const
       if (act) xn[r * n + lane] = o;
     }
     if (cost) {
-      real c = warp_sum(act ? large_cost_term(e.kind, p, xv, uv, false) : (real)0);
+      const real ct = large_cost_term(e.kind, p, xv, uv, false);
+      real c = warp_sum(act ? ct : (real)0);
       if (lane == 0) cost[r] = c;
     }
     if (fcost) {
-      real c = warp_sum(act ? large_cost_term(e.kind, p, xv, (real)0, true) : (real)0);
+      const real ct = large_cost_term(e.kind, p, xv, (real)0, true);
+      real c = warp_sum(act ? ct : (real)0);
       if (lane == 0) fcost[r] = c;
     }
   }
@@ -188,14 +199,18 @@ __global__ void __launch_bounds__(kThreads) kl_linearize(EnvLarge e, int64_t R, 
     real xv = act ? x[r * n + lane] : (real)0;
     real uv = (act && u) ? u[r * n + lane] : (real)0;
     if (l) {
-      real c = warp_sum(act ? large_cost_term(e.kind, p, xv, uv, final_only != 0) : (real)0);
+      const real ct = large_cost_term(e.kind, p, xv, uv, final_only != 0);
+      real c = warp_sum(act ? ct : (real)0);
       if (lane == 0) l[r] = c;
     }
     if (l_x && act) l_x[r * n + lane] = large_l_x(e.kind, p, xv);
-    if (l_u && act) l_u[r * n + lane] = (e.kind == TFMPC_ENV_HVAC) ? p[3] : (real)0;
+    const real beta_nl = __shfl_sync(FULL, p[1], 0);  // NavigationLQR: beta lives in lane 0 of row 1
+    if (l_u && act) l_u[r * n + lane] = (e.kind == TFMPC_ENV_HVAC) ? p[3] : (e.kind == TFMPC_ENV_NAVLQR ? (real)2 * beta_nl * uv : (real)0);
     // lane j computes column j of row i
     real diag;  // f_x[j][j] extra term of this lane
-    if (e.kind == TFMPC_ENV_RESERVOIR) {
+    if (e.kind == TFMPC_ENV_NAVLQR) {
+      diag = 1;
+    } else if (e.kind == TFMPC_ENV_RESERVOIR) {
       real cap = act ? p[0] : (real)1;
       real a = xv / cap;
       diag = (real)1 - (real)0.5 * (r_cos(a) * a + r_sin(a)) - uv;
@@ -204,7 +219,13 @@ __global__ void __launch_bounds__(kThreads) kl_linearize(EnvLarge e, int64_t R, 
     }
     for (int i = 0; i < n; i++) {
       real fx, fu;
-      if (e.kind == TFMPC_ENV_RESERVOIR) {  // f_x[i][j] = D[j][i] u_j (+diag), f_u[i][j] = D[j][i] x_j (- x_i on the diagonal)
+      real hxx = 0, huu = 0;  // second-order cost blocks (non-zero for NavigationLQR only)
+      if (e.kind == TFMPC_ENV_NAVLQR) {  // f_x = f_u = I, l_xx = 2I, l_uu = 2 beta I (lqr/navigation/__init__.py:30-47)
+        fx = (i == lane) ? (real)1 : (real)0;
+        fu = fx;
+        hxx = (i == lane) ? (real)2 : (real)0;
+        huu = (i == lane) ? (real)2 * beta_nl : (real)0;
+      } else if (e.kind == TFMPC_ENV_RESERVOIR) {  // f_x[i][j] = D[j][i] u_j (+diag), f_u[i][j] = D[j][i] x_j (- x_i on the diagonal)
         real d = act ? e.matB[lane * 32 + i] : (real)0;
         fx = d * uv + (i == lane ? diag : (real)0);
         fu = d * xv + (i == lane ? -xv : (real)0);
@@ -217,8 +238,8 @@ __global__ void __launch_bounds__(kThreads) kl_linearize(EnvLarge e, int64_t R, 
         int64_t o = (r * n + i) * n + lane;
         if (f_x) f_x[o] = fx;
         if (f_u) f_u[o] = fu;
-        if (l_xx) l_xx[o] = 0;
-        if (l_uu) l_uu[o] = 0;
+        if (l_xx) l_xx[o] = hxx;
+        if (l_uu) l_uu[o] = final_only ? (real)0 : huu;
         if (l_ux) l_ux[o] = 0;
         if (l_xu) l_xu[o] = 0;
       }
@@ -233,7 +254,7 @@ inline unsigned grid_warps(int64_t R) {
 }
 
 int check_large(const tfmpc_env *e) {
-  if (e->kind != TFMPC_ENV_RESERVOIR && e->kind != TFMPC_ENV_HVAC)
+  if (e->kind != TFMPC_ENV_RESERVOIR && e->kind != TFMPC_ENV_HVAC && e->kind != TFMPC_ENV_NAVLQR)
     return tfmpc_set_error(TFMPC_E_UNSUPPORTED, "no batched operator for environment kind %d with n=%d", e->kind, e->n);
   return TFMPC_OK;
 }

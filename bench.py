@@ -35,13 +35,14 @@ WORKLOADS = {
     "c3": ("C3 iLQR nonlinear navigation (nav.config.json, 2 zones, actions in [-1,1]) H=50", 65536, 50),
     "c4": ("C4 iLQR reservoir control, 20 reservoirs, H=40", 16384, 40),
     "c5s": ("C5 (single solve) iLQR HVAC 32 rooms 4x8 grid, H=48", 16384, 48),
+    "c5": ("C5 iLQR HVAC 32 rooms 4x8 grid, receding-horizon MPC loop: 48 plant steps, horizon 48-t", 16384, 48),
 }
 
 
 def workload_cfg(name):
     from tfmpc_b200.envs import synthetic
     return {"c3": synthetic.navigation_config, "c4": lambda: synthetic.reservoir_config(20),
-            "c5s": lambda: synthetic.hvac_grid_config(4, 8)}[name]()
+            "c5s": lambda: synthetic.hvac_grid_config(4, 8), "c5": lambda: synthetic.hvac_grid_config(4, 8)}[name]()
 
 
 def make_inputs(cfg, B, T, seed):
@@ -177,7 +178,7 @@ def run_reference(args):
     if rank != 0:
         return
     desc, _, T = WORKLOADS[args.workload]
-    sample = args.cpu_sample or {"c3": 65536, "c4": 512, "c5s": 128}[args.workload]
+    sample = args.cpu_sample or {"c3": 65536, "c4": 512, "c5s": 128, "c5": 128}[args.workload]
     for _ in range(args.warmup):
         cpu_baseline(args.workload, T, max(64, sample // 8))
     vals, secs, pis = [], 0.0, 0.0
@@ -244,12 +245,29 @@ def run_ours(args):
         if world > 1:   # the one collective of the sharded solve: per-problem total costs to every rank
             dist.all_gather(gathered[slot], outs[slot]["costs"].sum(1))
 
+    if args.workload == "c5":
+        # BASELINE config 5: the shrinking-horizon MPC loop of reference agents/mpc.py:10-15 + runners/__init__.py:14-43 for B
+        # plants at once: at plant step t re-solve over the remaining horizon T - t from fresh initial actions, apply the
+        # first action to the (deterministic) plant.  One bench "step" = the whole 48-step loop; stats are summed on the device.
+        mpc_stats = [torch.zeros(B, 4, dtype=torch.int32, device=dev) for _ in range(S)]
+        u_inits = [torch.from_numpy(make_inputs(cfg, B, T - t, seed=2000 + rank + t)[1]).to(dev) for t in range(T)]
+
+        def step(slot):  # noqa: F811
+            state = x0
+            mpc_stats[slot].zero_()
+            for t in range(T):
+                o = ops.ilqr_solve(nat, state, u_inits[t], opts)
+                mpc_stats[slot][:, :3] += o["stats"][:, :3] + torch.tensor([1, 0, 0], dtype=torch.int32, device=dev)
+                state, _ = ops.env_step(nat, state, o["actions"][:, 0].contiguous(), want_cost=False)
+            outs[slot]["stats"].copy_(mpc_stats[slot])
+            outs[slot]["stats"][:, 0] -= 1      # keep the "iteration index" convention: problem-iterations = stats[:,0] + 1
+
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(args.warmup, 3) if args.workload != "c5" else 1):
         step(0)
     for i in range(1, S):          # warm every stream's workspace
         with torch.cuda.stream(streams[i]):
@@ -310,11 +328,25 @@ def run_ours(args):
     nats = [envs.make_env(cfg).native() for _ in range(S)]
     houts = [new_out(host=True) for _ in range(S)]
 
+    if args.workload == "c5":
+        u_pins = [u.cpu().pin_memory() for u in u_inits]
+        applied = [torch.empty(B, T, m).pin_memory() for _ in range(S)]
+
     def e2e_worker(i, count):
         torch.cuda.set_device(local)
         with torch.cuda.stream(streams[i]):
             for _ in range(count):
-                ops.ilqr_solve_host(nats[i], x0_pin, u0_pin, opts, houts[i])
+                if args.workload == "c5":   # closed loop: inputs from pinned host memory, applied actions back to the host
+                    state = x0_pin.to(dev, non_blocking=True)
+                    acts = []
+                    for t in range(T):
+                        o = ops.ilqr_solve(nats[i], state, u_pins[t].to(dev, non_blocking=True), opts)
+                        acts.append(o["actions"][:, 0])
+                        state, _ = ops.env_step(nats[i], state, o["actions"][:, 0].contiguous(), want_cost=False)
+                    applied[i].copy_(torch.stack(acts, dim=1), non_blocking=True)
+                    torch.cuda.current_stream().synchronize()
+                else:
+                    ops.ilqr_solve_host(nats[i], x0_pin, u0_pin, opts, houts[i])
 
     for i in range(S):
         e2e_worker(i, 1)                   # warm (allocates each handle's cached device scratch)
@@ -334,13 +366,16 @@ def run_ours(args):
     e2e_value = pi_all * e2e_steps / float(te[0])
     h2d = x0_pin.numel() * 4 + u0_pin.numel() * 4
     d2h = sum(v.numel() * 4 for v in houts[0].values())
+    if args.workload == "c5":
+        h2d = x0_pin.numel() * 4 + sum(u.numel() * 4 for u in u_pins)
+        d2h = applied[0].numel() * 4
 
     if rank == 0:
         peaks, peak_src = measured_peaks()
         lib = _native.load("f32")
         tf, kms = ctypes.c_double(), ctypes.c_double()
         lib.tfmpc_measure_fp32_peak(ctypes.byref(tf), ctypes.byref(kms))
-        flops, byts = algorithmic_work(args.workload, T, stats)
+        flops, byts = algorithmic_work(args.workload, T if args.workload != "c5" else (T + 1) / 2.0, stats)
         solve_s = total_ms * 1e-3 / args.steps             # device time per solve (launch sequence), pipelined if S > 1
         ach_tf, ach_gb = flops / solve_s / 1e12, byts / solve_s / 1e9
         fp32 = {"bound": "fp32", "achieved": ach_tf, "peak": tf.value, "unit": "TFLOP/s", "frac": ach_tf / tf.value if tf.value else None,
@@ -350,7 +385,7 @@ def run_ours(args):
         primary = fp32 if (fp32["frac"] or 0) >= hbm["frac"] else hbm
         roofline = dict(primary)
         roofline["kernel"] = ("launch sequence of one solve: k_tick_backward + k_tick_linesearch per tick (thread-per-problem)"
-                              if args.workload == "c3" else "kw_solve (lane-per-state, persistent)")
+                              if args.workload == "c3" else "kw_solve (lane-per-state, persistent)" + (" x 48 plant steps" if args.workload == "c5" else ""))
         roofline["algorithmic_flops_per_solve"] = flops
         roofline["algorithmic_bytes_per_solve"] = byts
         roofline["other"] = hbm if primary is fp32 else fp32
@@ -374,10 +409,11 @@ def run_ours(args):
                 "roofline": roofline,
                 "e2e": {"value": e2e_value, "unit": "problem-iterations/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "steps": e2e_steps, "host_threads": S,
-                        "api": "tfmpc_ilqr_solve_host (pinned host buffers in, host buffers out, synchronous), one call per step"},
+                        "api": ("tfmpc_ilqr_solve_host (pinned host buffers in, host buffers out, synchronous), one call per step" if args.workload != "c5"
+                                else "MPC loop: x0 and every step's initial actions copied from pinned host memory, applied actions copied back")},
                 "gpu_launches": int(launches), "clocks": clocks}
         if world == 1 and not args.no_cpu_baseline:
-            sample = args.cpu_sample or {"c3": 65536, "c4": 512, "c5s": 128}[args.workload]
+            sample = args.cpu_sample or {"c3": 65536, "c4": 512, "c5s": 128, "c5": 128}[args.workload]
             v, cores, pi, dt = cpu_baseline(args.workload, T, sample)
             line["cpu_baseline"] = {"value": v, "unit": "problem-iterations/s", "cores": cores, "kind": "port",
                                     "sample": f"{sample} problems of the same workload ({pi:.0f} problem-iterations in {dt:.1f} s), "

@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(kThreads) k_forward(EnvSmall e, int64_t B, int
 // trajectory buffers.  Converged problems drop out of the list, so late ticks touch few problems and
 // cost only their launch latency.
 constexpr int GA = 4;            // line-search lanes (and candidate buffers) per problem
-constexpr int NBUF = 1 + GA;
+constexpr int NBUF = 2 * GA;      // two candidate sets of GA trajectories; the nominal is one member of the set not being written
 constexpr int kExtraTicks = 24;  // ticks beyond max_iterations available to regularisation retries (ilqr.py:267-270)
 
 struct WS {  // carve-up of the workspace
@@ -86,7 +86,8 @@ struct WS {  // carve-up of the workspace
   int *iteration, *n_bwd, *n_fwd, *status, *cur, *phase, *guard;
   double *mu, *delta;
   real *J_hat, *dV1, *dV2;
-  R4 *traj;                      // NBUF buffers x (T+1) records x CHn chunks x S slots
+  R4 *traj;                      // [set 0..1][(T+1) records x CHn chunks][S slots][GA lanes]: the GA candidates of one
+                                 // (problem, timestep) are 64 contiguous bytes, so a line-search group writes full sectors
   R4 *gain;                      // T records x CHg chunks x S slots
   real *cost;                    // (T+1) rows x S
   int64_t S, traj_chunks;        // traj_chunks = (T+1) * CHn
@@ -120,9 +121,11 @@ inline WS carve(void *ws, int64_t S, int T, int N, int M) {
   return w;
 }
 
+// trajectory buffer `buf` = set * GA + lane of problem slot b
 template <int N, int M>
 __device__ __forceinline__ VecTraj<N, M> buf_traj(const WS &w, int buf, int64_t b) {
-  return VecTraj<N, M>{w.traj + (int64_t)buf * w.traj_chunks * w.S + b, w.S};
+  const int set = buf / GA, ln = buf % GA;
+  return VecTraj<N, M>{w.traj + ((int64_t)set * w.traj_chunks * w.S + b) * GA + ln, w.S * GA};
 }
 template <int N, int M>
 __device__ __forceinline__ VecGain<N, M> buf_gain(const WS &w, int64_t b) {
@@ -200,7 +203,8 @@ __global__ void __launch_bounds__(kThreads) k_tick_linesearch(EnvSmall e, IlqrOp
     int rollouts = 0, cand = 0;
     const VecTraj<N, M> nom = buf_traj<N, M>(w, p.cur, b);
     const VecGain<N, M> gain = buf_gain<N, M>(w, b);
-    const int mybuf = la + (la >= p.cur ? 1 : 0);  // this lane's candidate buffer: the la-th buffer that is not the nominal
+    const int cset = 1 - p.cur / GA;               // candidates go to the set that does not hold the nominal
+    const int mybuf = cset * GA + la;
     const VecTraj<N, M> mine = buf_traj<N, M>(w, mybuf, b);
     for (int pass = 0; pass < PASSES; pass++) {
       if (!__any_sync(FULL, searching)) break;
@@ -219,7 +223,7 @@ __global__ void __launch_bounds__(kThreads) k_tick_linesearch(EnvSmall e, IlqrOp
       const real r_src = __shfl_sync(FULL, res, src, GA);
       if (searching) {
         residual = r_src;
-        cand = src + (src >= p.cur ? 1 : 0);
+        cand = cset * GA + src;
         if (gm) { accept = true; rollouts = pass * GA + src + 1; searching = false; }
         else { rollouts = pass * GA + last + 1; if (pass == PASSES - 1) searching = false; }
       }
@@ -275,7 +279,7 @@ __global__ void __launch_bounds__(128) k_transpose_out(int64_t B, int T, WS w, i
   const int64_t b = slot0 + lane;
   const bool vb = b < B;
   const real *rec = nullptr;
-  if (which < 2 && vb) rec = reinterpret_cast<const real *>(w.traj + (int64_t)w.cur[b] * w.traj_chunks * w.S + b);
+  if (which < 2 && vb) rec = reinterpret_cast<const real *>(buf_traj<N, M>(w, w.cur[b], b).base);
   for (int r0 = 0; r0 < nrows; r0 += 32) {
 #pragma unroll 4
     for (int rr = 0; rr < 32; rr++) {
@@ -285,7 +289,7 @@ __global__ void __launch_bounds__(128) k_transpose_out(int64_t B, int T, WS w, i
         if (which == 2) v = w.cost[(int64_t)r * w.S + b];
         else {
           const int t = which == 0 ? r / N : r / M, j = which == 0 ? r % N : N + r % M;
-          v = rec[((int64_t)(t * CH + (j >> 2)) * w.S) * 4 + (j & 3)];
+          v = rec[((int64_t)(t * CH + (j >> 2)) * w.S * GA) * 4 + (j & 3)];
         }
         tile[wq][rr][lane] = v;
       }

@@ -269,11 +269,11 @@ def run_ours(args):
 
     for _ in range(max(args.warmup, 3) if args.workload != "c5" else 1):
         step(0)
-    for i in range(1, S):          # warm every stream's workspace
+    for i in range(S):             # warm every stream's workspace (the caching allocator keeps one pool per stream)
         with torch.cuda.stream(streams[i]):
             step(i)
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
+    sampler = ClockSampler(local) if rank == 0 and not args.no_clock_sampler else None
     t_wall0 = time.time()
 
     # ---- (1) sequential: one batch at a time, L2 flushed between steps -> per-batch latency
@@ -296,9 +296,30 @@ def run_ours(args):
     e0.record(main)
     for st in streams:
         st.wait_event(e0)
-    for s in range(args.steps):
-        with torch.cuda.stream(streams[s % S]):
-            step(s % S)
+    tl = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    if args.issue == "threads" and S > 1:      # one issuing host thread per stream (ctypes drops the GIL inside the C call)
+        def issue(i):
+            torch.cuda.set_device(local)
+            with torch.cuda.stream(streams[i]):
+                for k in range(i, args.steps, S):
+                    if args.timeline:
+                        tl[k][0].record()
+                    step(i)
+                    if args.timeline:
+                        tl[k][1].record()
+        workers = [threading.Thread(target=issue, args=(i,)) for i in range(S)]
+        for th in workers:
+            th.start()
+        for th in workers:
+            th.join()
+    else:
+        for s in range(args.steps):
+            with torch.cuda.stream(streams[s % S]):
+                if args.timeline:
+                    tl[s][0].record()
+                step(s % S)
+                if args.timeline:
+                    tl[s][1].record()
     for st in streams:
         done = torch.cuda.Event()
         done.record(st)
@@ -306,6 +327,7 @@ def run_ours(args):
     e1.record(main)
     barrier()
     pipe_ms = float(e0.elapsed_time(e1))
+    timeline = [[k % S, round(e0.elapsed_time(a), 3), round(e0.elapsed_time(b), 3)] for k, (a, b) in enumerate(tl)] if args.timeline else None
     launches = _native.kernel_launch_count("f32") - launches0
     t_wall1 = time.time()
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
@@ -406,6 +428,7 @@ def run_ours(args):
                            "status_histogram": np.bincount(stats[:, 3], minlength=5).tolist()},
                 "sequential": {"value": pi_all * args.steps / (seq_ms * 1e-3), "unit": "problem-iterations/s",
                                "latency_ms_per_batch": seq_ms / args.steps, "step_ms": step_ms},
+                "pipeline_timeline_ms": {"columns": ["stream", "start", "end"], "steps": timeline},
                 "roofline": roofline,
                 "e2e": {"value": e2e_value, "unit": "problem-iterations/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "steps": e2e_steps, "host_threads": S,
@@ -434,6 +457,9 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="problems per GPU (default: the workload's BASELINE batch)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="problems in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--timeline", action="store_true", help="record start/end events around every pipelined step")
+    ap.add_argument("--no-clock-sampler", action="store_true", help="diagnostics only: a line without `clocks` is not a valid bench line")
+    ap.add_argument("--issue", default="single", choices=["threads", "single"], help="host threads issuing the pipelined steps")
     ap.add_argument("--streams", type=int, default=8, help="CUDA streams the independent steps are pipelined over (1 = strictly sequential)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -36,8 +36,9 @@ static void run(const EnvSmall &e, const IlqrOpts &o, int64_t B, int T, const re
   std::vector<R4> ws((size_t)(2 * nomch + gch) * S);
   const int64_t nx = (int64_t)(T + 1) * N, nu = (int64_t)T * M;
   for (int64_t b = 0; b < B; b++) {
-    VecTraj<N, M> traj[2] = {{ws.data() + b, S}, {ws.data() + nomch * S + b, S}};
-    VecGain<N, M> gain = {ws.data() + 2 * nomch * S + b, S};
+    const int64_t chn = VecTraj<N, M>::CH, chg = VecGain<N, M>::CH;
+    VecTraj<N, M> traj[2] = {{ws.data() + b, chn * S, S}, {ws.data() + nomch * S + b, chn * S, S}};   // [t][chunk][slot]
+    VecGain<N, M> gain = {ws.data() + 2 * nomch * S + b * chg, S * chg, 1};                           // [t][slot][chunk]
     const CostSink none = {nullptr, 0};
     start_pass<KIND, N, M>(e, T, x0 + b * N, u_init + b * nu, traj[0], none);
     int cur = solve_one<KIND, N, M>(e, o, T, traj, gain, stats + b * 4);

@@ -40,7 +40,8 @@ _PyCapsule_GetPointer.argtypes = [C.py_object, C.c_char_p]
 
 
 def lib_path(precision="f32"):
-    return os.path.join(_LIBDIR, "libtfmpc_b200.so" if precision == "f32" else "libtfmpc_b200_f64.so")
+    # TFMPC_B200_LIBDIR: load another build of the same sources (A/B experiments); never a different implementation
+    return os.path.join(os.environ.get("TFMPC_B200_LIBDIR", _LIBDIR), "libtfmpc_b200.so" if precision == "f32" else "libtfmpc_b200_f64.so")
 
 
 def load(precision="f32"):

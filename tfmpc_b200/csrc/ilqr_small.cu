@@ -88,7 +88,7 @@ struct WS {  // carve-up of the workspace
   real *J_hat, *dV1, *dV2;
   R4 *traj;                      // [set 0..1][(T+1) records x CHn chunks][S slots][GA lanes]: the GA candidates of one
                                  // (problem, timestep) are 64 contiguous bytes, so a line-search group writes full sectors
-  R4 *gain;                      // T records x CHg chunks x S slots
+  R4 *gain;                      // [T records][S slots][CHg chunks]: one problem-step of gains = one 32-byte sector (n=m=2)
   real *cost;                    // (T+1) rows x S
   int64_t S, traj_chunks;        // traj_chunks = (T+1) * CHn
 };
@@ -125,11 +125,11 @@ inline WS carve(void *ws, int64_t S, int T, int N, int M) {
 template <int N, int M>
 __device__ __forceinline__ VecTraj<N, M> buf_traj(const WS &w, int buf, int64_t b) {
   const int set = buf / GA, ln = buf % GA;
-  return VecTraj<N, M>{w.traj + ((int64_t)set * w.traj_chunks * w.S + b) * GA + ln, w.S * GA};
+  return VecTraj<N, M>{w.traj + ((int64_t)set * w.traj_chunks * w.S + b) * GA + ln, VecTraj<N, M>::CH * w.S * GA, w.S * GA};
 }
 template <int N, int M>
 __device__ __forceinline__ VecGain<N, M> buf_gain(const WS &w, int64_t b) {
-  return VecGain<N, M>{w.gain + b, w.S};
+  return VecGain<N, M>{w.gain + b * VecGain<N, M>::CH, w.S * VecGain<N, M>::CH, 1};
 }
 
 __device__ __forceinline__ void load_prob(const WS &w, int64_t b, Prob &p) {

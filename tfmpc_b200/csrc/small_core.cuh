@@ -629,11 +629,11 @@ HD int backward_step(const EnvSmall &e, const Lin<N, M> &L, const real *u, real 
 // Two implementations:
 //  * Strided*  -- plain arrays addressed as base[row * stride]; stride 1 = the reference's dense [T, n] layout of one
 //                 problem (stage kernels, host emulation).
-//  * Vec*      -- the solve workspace: 16-byte (4 x real) chunks, chunk-major then problem slot, i.e.
-//                 chunk[(t * CH + c) * S + slot].  One timestep of one problem is CH consecutive-in-t vector words, so a
-//                 thread moves it with CH 128-bit accesses (LDG.128 / STG.128), a warp of adjacent slots covers 512
-//                 contiguous bytes per access, and a lone problem still uses half of every 32-byte sector it touches
-//                 (the scalar struct-of-arrays layout used 4 of 32 bytes once the active list is no longer contiguous).
+//  * Vec*      -- the solve workspace: 16-byte (4 x real) chunks addressed as base[t * ts + c * cs].  One timestep of one
+//                 problem moves with CH 128-bit accesses (LDG.128 / STG.128).  The kernels choose the strides so that what
+//                 one access pattern touches together is contiguous: nominal trajectories [t][slot] (a warp of adjacent
+//                 problems reads 512 contiguous bytes), gains [t][slot][chunk] (one problem-step = one 32-byte sector),
+//                 line-search candidates [t][slot][lane] (the 4 candidates of a problem-step = two full sectors).
 struct alignas(4 * sizeof(real)) R4 { real v[4]; };
 
 template <int N, int M>
@@ -680,37 +680,38 @@ struct StridedGain {
   }
 };
 
+// record t, chunk c lives at base[t * ts + c * cs] (ts, cs in R4 units)
 template <int CNT>
-HD void vec_load(const R4 *base, int64_t S, int t, real *out) {  // CNT reals of record t
+HD void vec_load(const R4 *base, int64_t ts, int64_t cs, int t, real *out) {  // CNT reals of record t
   constexpr int CH = (CNT + 3) / 4;
 #pragma unroll
   for (int c = 0; c < CH; c++) {
-    const R4 r = base[(int64_t)(t * CH + c) * S];
+    const R4 r = base[(int64_t)t * ts + c * cs];
 #pragma unroll
     for (int j = 0; j < 4; j++)
       if (c * 4 + j < CNT) out[c * 4 + j] = r.v[j];
   }
 }
 template <int CNT>
-HD void vec_store(R4 *base, int64_t S, int t, const real *in) {
+HD void vec_store(R4 *base, int64_t ts, int64_t cs, int t, const real *in) {
   constexpr int CH = (CNT + 3) / 4;
 #pragma unroll
   for (int c = 0; c < CH; c++) {
     R4 r;
 #pragma unroll
     for (int j = 0; j < 4; j++) r.v[j] = (c * 4 + j < CNT) ? in[c * 4 + j] : (real)0;
-    base[(int64_t)(t * CH + c) * S] = r;
+    base[(int64_t)t * ts + c * cs] = r;
   }
 }
 
 template <int N, int M>
 struct VecTraj {     // record t = [x (N), u (M)]
-  R4 *base;          // already offset to this problem's slot
-  int64_t S;
+  R4 *base;          // already offset to this problem's slot (and candidate lane)
+  int64_t ts, cs;    // strides between timesteps / between the chunks of one record
   static constexpr int CH = (N + M + 3) / 4;
   HD void load_xu(int t, real *x, real *u) const {
     real r[N + M];
-    vec_load<N + M>(base, S, t, r);
+    vec_load<N + M>(base, ts, cs, t, r);
 #pragma unroll
     for (int i = 0; i < N; i++) x[i] = r[i];
 #pragma unroll
@@ -718,7 +719,7 @@ struct VecTraj {     // record t = [x (N), u (M)]
   }
   HD void load_x(int t, real *x) const {
     real r[N + M];
-    vec_load<N + M>(base, S, t, r);
+    vec_load<N + M>(base, ts, cs, t, r);
 #pragma unroll
     for (int i = 0; i < N; i++) x[i] = r[i];
   }
@@ -728,7 +729,7 @@ struct VecTraj {     // record t = [x (N), u (M)]
     for (int i = 0; i < N; i++) r[i] = x[i];
 #pragma unroll
     for (int i = 0; i < M; i++) r[N + i] = u[i];
-    vec_store<N + M>(base, S, t, r);
+    vec_store<N + M>(base, ts, cs, t, r);
   }
   HD void store_x(int t, const real *x) const {
     real r[N + M];
@@ -736,18 +737,18 @@ struct VecTraj {     // record t = [x (N), u (M)]
     for (int i = 0; i < N; i++) r[i] = x[i];
 #pragma unroll
     for (int i = 0; i < M; i++) r[N + i] = 0;
-    vec_store<N + M>(base, S, t, r);
+    vec_store<N + M>(base, ts, cs, t, r);
   }
 };
 
 template <int N, int M>
 struct VecGain {     // record t = [K (M*N), k (M)]
   R4 *base;
-  int64_t S;
+  int64_t ts, cs;
   static constexpr int CH = (M * N + M + 3) / 4;
   HD void load(int t, real *Kt, real *kt) const {
     real r[M * N + M];
-    vec_load<M * N + M>(base, S, t, r);
+    vec_load<M * N + M>(base, ts, cs, t, r);
 #pragma unroll
     for (int i = 0; i < M * N; i++) Kt[i] = r[i];
 #pragma unroll
@@ -759,7 +760,7 @@ struct VecGain {     // record t = [K (M*N), k (M)]
     for (int i = 0; i < M * N; i++) r[i] = Kt[i];
 #pragma unroll
     for (int i = 0; i < M; i++) r[M * N + i] = kt[i];
-    vec_store<M * N + M>(base, S, t, r);
+    vec_store<M * N + M>(base, ts, cs, t, r);
   }
 };
 

@@ -180,6 +180,90 @@ __global__ void __launch_bounds__(kThreads) k_tick_backward(EnvSmall e, IlqrOpts
   }
 }
 
+// ---- line-search rollout with the nominal / gain records staged through shared memory
+// The rollout is a dependent chain (x_{t+1} needs x_t), one step is ~100 instructions, and every step needs 48 bytes
+// (n = m = 2) of nominal + gains that live in HBM: ncu showed the register-ring prefetch of forward_pass() reaching
+// only ~1.5 steps ahead and >50% of the kernel's stall samples waiting on those loads.  Here the GA lanes of a problem
+// share one copy of each record, fetched Ring::depth (8) steps ahead by cp.async (LDGSTS) into a per-warp shared-memory ring, so
+// the loads hold no registers and the prefetch distance covers a DRAM round trip.
+template <int N, int M>
+struct Ring {   // depth: 8 steps, fewer when the records are large (static shared memory budget of 32 KB per CTA)
+  static constexpr int CHT = VecTraj<N, M>::CH + VecGain<N, M>::CH;
+  static constexpr int slot_bytes = (kThreads / 32) * (32 / 4) * CHT * (int)sizeof(R4);
+  static constexpr int depth = 32768 / slot_bytes >= 8 ? 8 : (32768 / slot_bytes >= 4 ? 4 : 2);
+};
+
+__device__ __forceinline__ void cp_async_r4(R4 *dst_smem, const R4 *src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+#pragma unroll
+  for (int o = 0; o < (int)sizeof(R4); o += 16)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d + o), "l"((const char *)src + o) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int PENDING>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(PENDING) : "memory"); }
+
+// One rollout per lane (forward_pass semantics, ilqr.py:174-212); the GA lanes of a group share ring[..][sub][..].
+// Called by all 32 lanes of the warp; `fetch`: this lane's group still searches (its records are staged), `run`: this
+// lane has a step size to try.
+template <int KIND, int N, int M>
+__device__ __forceinline__ void rollout_staged(const EnvSmall &e, int T, const VecTraj<N, M> &nom, const VecGain<N, M> &gain, real alpha,
+                                               const VecTraj<N, M> &out, R4 (*ring)[32 / GA][VecTraj<N, M>::CH + VecGain<N, M>::CH],
+                                               int sub, int la, bool fetch, bool run, real &J, real &residual) {
+  constexpr int CHn = VecTraj<N, M>::CH, CHg = VecGain<N, M>::CH, CHT = CHn + CHg, kRing = Ring<N, M>::depth;
+  constexpr unsigned FULL = 0xffffffffu;
+  const CostSink none = {nullptr, 0};
+  auto issue = [&](int t) {
+    if (fetch && t < T) {
+#pragma unroll
+      for (int c = la; c < CHT; c += GA) {
+        const R4 *src = c < CHn ? nom.base + (int64_t)t * nom.ts + c * nom.cs : gain.base + (int64_t)t * gain.ts + (c - CHn) * gain.cs;
+        cp_async_r4(&ring[t % kRing][sub][c], src);
+      }
+    }
+    cp_async_commit();   // one group per step on every lane, empty or not, so that wait_group counts steps
+  };
+#pragma unroll
+  for (int d = 0; d < kRing; d++) issue(d);
+  real x[N];
+  J = 0; residual = 0;
+  for (int t = 0; t < T; t++) {
+    cp_async_wait<kRing - 1>();
+    __syncwarp(FULL);                      // every lane's share of step t has landed
+    NomRec<N, M> r;
+    {
+      real v[4 * CHT];
+      const R4 *rec = ring[t % kRing][sub];
+#pragma unroll
+      for (int c = 0; c < CHT; c++) {
+        const R4 q = rec[c];
+#pragma unroll
+        for (int j = 0; j < 4; j++) v[4 * c + j] = q.v[j];
+      }
+#pragma unroll
+      for (int i = 0; i < N; i++) r.xh[i] = v[i];
+#pragma unroll
+      for (int i = 0; i < M; i++) r.uh[i] = v[N + i];
+#pragma unroll
+      for (int i = 0; i < M * N; i++) r.K[i] = v[4 * CHn + i];
+#pragma unroll
+      for (int i = 0; i < M; i++) r.k[i] = v[4 * CHn + M * N + i];
+    }
+    __syncwarp(FULL);                      // slot t % kRing is free again
+    issue(t + kRing);
+    if (t == 0) {
+#pragma unroll
+      for (int i = 0; i < N; i++) x[i] = r.xh[i];
+    }
+    if (run) forward_step<KIND, N, M>(e, alpha, r, t, x, out, none, J, residual);
+  }
+  cp_async_wait<0>();
+  if (run) {
+    out.store_x(T, x);
+    J += env_final_cost<KIND, N, M>(e, x);
+  }
+}
+
 template <int KIND, int N, int M>
 __global__ void __launch_bounds__(kThreads) k_tick_linesearch(EnvSmall e, IlqrOpts o, int T, WS w, int parity) {
   constexpr unsigned FULL = 0xffffffffu;
@@ -190,7 +274,7 @@ __global__ void __launch_bounds__(kThreads) k_tick_linesearch(EnvSmall e, IlqrOp
   const int lane = threadIdx.x & 31, la = lane % GA, sub = lane / GA;
   const int groups_per_warp = 32 / GA;
   const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-  const CostSink none = {nullptr, 0};
+  __shared__ R4 ring[kThreads / 32][Ring<N, M>::depth][32 / GA][Ring<N, M>::CHT];
   for (int base = warp_global * groups_per_warp; base < cnt; base += nwarps * groups_per_warp) {  // warp-uniform trip count
     const int gi = base + sub;
     const bool valid = gi < cnt;
@@ -212,11 +296,9 @@ __global__ void __launch_bounds__(kThreads) k_tick_linesearch(EnvSmall e, IlqrOp
       const bool run = searching && ai < N_ALPHA;
       real J = 0, res = 0;
       bool acc = false;
-      if (run) {
-        const real alpha = o.alphas[ai];
-        forward_pass<KIND, N, M>(e, T, nom, gain, alpha, mine, none, J, res);
-        acc = ls_accepts(o, alpha, p.J_hat, p.dV1, p.dV2, J);
-      }
+      const real alpha = o.alphas[run ? ai : 0];
+      rollout_staged<KIND, N, M>(e, T, nom, gain, alpha, mine, ring[threadIdx.x >> 5], sub, la, searching, run, J, res);
+      if (run) acc = ls_accepts(o, alpha, p.J_hat, p.dV1, p.dV2, J);
       const unsigned gm = (__ballot_sync(FULL, acc) >> (sub * GA)) & ((1u << GA) - 1u);
       const int last = min(GA - 1, N_ALPHA - 1 - pass * GA);      // last alpha lane of this pass
       const int src = gm ? (__ffs(gm) - 1) : last;                 // first accepted lane, else the last candidate

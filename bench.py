@@ -32,6 +32,7 @@ if ROOT not in sys.path:
 
 WORKLOADS = {
     # name: (description, batch per GPU, horizon)
+    "c2": ("C2 navlin linear-navigation LQR, beta=5.0, H=10, random (x0, goal) pairs", 65536, 10),
     "c3": ("C3 iLQR nonlinear navigation (nav.config.json, 2 zones, actions in [-1,1]) H=50", 65536, 50),
     "c4": ("C4 iLQR reservoir control, 20 reservoirs, H=40", 16384, 40),
     "c5s": ("C5 (single solve) iLQR HVAC 32 rooms 4x8 grid, H=48", 16384, 48),
@@ -173,11 +174,141 @@ def reference_under_shim(name, T, problems=3):
             "iterations": d["iterations"]}
 
 
+def c2_inputs(B, seed):
+    rng = np.random.RandomState(seed)
+    return rng.uniform(-10, 10, size=(B, 2)).astype(np.float32), rng.normal(size=(B, 2)).astype(np.float32)
+
+
+def c2_cpu(B, T, threads=0):
+    """CPU arm of C2: the oracle's LQR (C, OpenMP over problems).  Returns (problems/s, cores, seconds)."""
+    from oracle import oracle
+    o = oracle.Oracle("f32")
+    goal, x0 = c2_inputs(B, 12345)
+    F = np.concatenate([np.eye(2), np.eye(2)], axis=1)
+    c = np.concatenate([-2 * goal, np.zeros_like(goal)], axis=1)
+    cores = o.max_threads() if threads <= 0 else threads
+    t0 = time.perf_counter()
+    o.lqr_solve(F, np.zeros(2), np.diag([2.0, 2.0, 10.0, 10.0]), c, x0, T, nthreads=cores)
+    dt = time.perf_counter() - t0
+    return B / dt, cores, dt
+
+
+def run_c2(args):
+    """BASELINE config C2: one LQR solve (backward Riccati sweep + forward rollout, policy and value function returned, as
+    reference LQR.backward + LQR.forward do) per problem; a step = one batch of B problems.  The kernel is HBM-bound:
+    24 bytes in, 760 bytes out per problem."""
+    import torch
+    import torch.distributed as dist
+
+    from tfmpc_b200 import _native, envs, ops
+
+    rank, local, world = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("LOCAL_RANK", "0"), ("WORLD_SIZE", "1")))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    desc, B, T = WORKLOADS["c2"]
+    B = args.batch or B
+    goal_h, x0_h = c2_inputs(B, 1000 + rank)
+    solver = envs.make_lqr_linear_navigation(goal_h, 5.0)
+    x0_pin = torch.from_numpy(x0_h).pin_memory()
+    x0 = x0_pin.to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    Fd, fd, Cd, cd = solver._device_params()
+    out = ops.lqr_solve(Fd, fd, Cd, cd, x0, T)
+
+    def step():
+        return ops.lqr_solve(Fd, fd, Cd, cd, x0, T, out=out)   # trajectory + policy + value function, results reused in place
+
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
+    for _ in range(max(3, args.warmup)):
+        out = step()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    t_wall0 = time.time()
+    launches0 = _native.kernel_launch_count("f32")
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for a, b in ev:
+        flush.zero_()
+        a.record()
+        out = step()
+        b.record()
+    barrier()
+    launches = _native.kernel_launch_count("f32") - launches0
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    t = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t[0])
+    value = B * world * args.steps / (total_ms * 1e-3)
+    # end to end: host buffers in, host buffers out (trajectory only, what LQR.solve returns)
+    F, f, Cm, c = (t.cpu() for t in (Fd, fd, Cd, cd))
+    c_pin = c.pin_memory() if c.dim() == 2 else c
+    ho = {k: v.pin_memory() for k, v in ops.lqr_solve_host(F, f, Cm, c_pin, x0_pin, T).items()}
+    ops.lqr_solve_host(F, f, Cm, c_pin, x0_pin, T, out=ho)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ops.lqr_solve_host(F, f, Cm, c_pin, x0_pin, T, out=ho)
+    barrier()
+    te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    clocks = sampler.stop(t_wall0, time.time()) if sampler else None
+    if rank == 0:
+        peaks, peak_src = measured_peaks()
+        byts = B * (24 + 4 * ((T + 1) * 2 + T * 2 + (T + 1) + 1 + T * (4 + 2 + 4 + 2 + 1)))
+        ach = byts / (total_ms / args.steps * 1e-3) / 1e9
+        line = {"metric": "batched LQR problems/sec", "value": value, "unit": "problems/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": desc, "batch_per_gpu": B, "global_batch": B * world, "horizon": T, "state_dim": 2, "action_dim": 2,
+                           "parallelism": f"batch sharded over {world} GPU(s), no data-path collective",
+                           "l2": "256 MB buffer written between timed iterations (untimed L2 flush)",
+                           "status_nonzero": int((out["status"] != 0).sum())},
+                "step_ms": step_ms,
+                "roofline": {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
+                             "traffic": None, "peak_source": peak_src, "kernel": "k_lqr_small<2,2> (thread per problem, backward + forward fused)",
+                             "algorithmic_bytes_per_problem": byts // B},
+                "e2e": {"value": B * world * args.steps / float(te[0]), "unit": "problems/s", "h2d_bytes_per_step": int(x0_pin.numel() * 4 + c.numel() * 4),
+                        "d2h_bytes_per_step": int(sum(v.numel() * 4 for v in ho.values())), "api": "tfmpc_lqr_solve_host (pinned host buffers in and out, synchronous), one call per step"},
+                "gpu_launches": int(launches), "clocks": clocks}
+        if world == 1 and not args.no_cpu_baseline:
+            v, cores, dt = c2_cpu(args.cpu_sample or B, T)
+            line["cpu_baseline"] = {"value": v, "unit": "problems/s", "cores": cores, "kind": "port",
+                                    "sample": f"{args.cpu_sample or B} problems in {dt:.2f} s, C/OpenMP restatement of reference LQR (oracle/)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     desc, _, T = WORKLOADS[args.workload]
+    if args.workload == "c2":
+        B = args.cpu_sample or args.batch or WORKLOADS["c2"][1]
+        for _ in range(args.warmup):
+            c2_cpu(B, T)
+        secs = 0.0
+        for _ in range(args.steps):
+            v, cores, dt = c2_cpu(B, T)
+            secs += dt
+        value = B * args.steps / secs
+        print(json.dumps({"impl": "reference", "metric": "batched LQR problems/sec", "value": value, "unit": "problems/s", "n_gpus": args.gpus,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True,
+                          "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": desc, "batch_per_step": B, "horizon": T},
+                          "cpu_baseline": {"value": value, "unit": "problems/s", "cores": cores, "kind": "port",
+                                           "sample": f"{B} problems per step, {args.steps} steps"},
+                          "e2e": {"value": value, "unit": "problems/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}), flush=True)
+        return
     sample = args.cpu_sample or {"c3": 65536, "c4": 512, "c5s": 128, "c5": 128}[args.workload]
     for _ in range(args.warmup):
         cpu_baseline(args.workload, T, max(64, sample // 8))
@@ -464,6 +595,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "c2":
+        run_c2(args)
     else:
         run_ours(args)
 

@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include <mutex>
 
 // ------------------------------------------------------------------ errors / counters
 static thread_local char g_err[512] = "";
@@ -413,6 +414,17 @@ int tfmpc_lqr_solve_host(int64_t B, int n, int m, int T, const real *F, int64_t 
   int64_t bx = al(B * n * sizeof(real)), bs = al(B * (T + 1) * n * sizeof(real)), ba = al(B * T * m * sizeof(real)), bco = al(B * (T + 1) * sizeof(real));
   int64_t bst = al(B * sizeof(int32_t));
   char *base = nullptr;
+  {  // keep freed stream-ordered memory in the pool across calls (the default threshold of 0 returns it to the OS at every sync)
+    static std::once_flag pool_once[64];
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    std::call_once(pool_once[dev & 63], [dev] {
+      cudaMemPool_t pool;
+      uint64_t keep = ~0ull;
+      if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+      cudaGetLastError();
+    });
+  }
   CUDA_TRY(cudaMallocAsync((void **)&base, bF + bf + bC + bc + bx + bs + ba + bco + bst, s));
   char *p = base;
   real *dF = (real *)p; p += bF; real *df = (real *)p; p += bf; real *dC = (real *)p; p += bC; real *dc = (real *)p; p += bc;

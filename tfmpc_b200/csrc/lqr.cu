@@ -53,16 +53,121 @@ __device__ __forceinline__ int inverse_small(const real *A, real *inv) {
   return fail;
 }
 
+// ---- output sinks of the thread-per-problem solve
+// DirectOut: every thread writes its own rows of the reference-layout outputs [B, T, ...] (a problem's row is contiguous,
+//            neighbouring threads are a whole row apart -> scattered 4-byte stores; the fallback for long rows).
+// TileOut:   the 32 problems of a warp own one CONTIGUOUS block of every output array (32 consecutive rows), so the warp
+//            assembles each block in shared memory and one lane writes it with a TMA bulk store (cp.async.bulk
+//            shared -> global): full-line HBM writes, no per-element store instructions, and the gains never leave
+//            the SM between the backward sweep and the rollout.
 template <int N, int M>
-__global__ void __launch_bounds__(kThreads) k_lqr_small(int64_t B, int T, const real *__restrict__ Fp, int64_t sF, const real *__restrict__ fp,
-                                                        int64_t sf, const real *__restrict__ Cp, int64_t sC, const real *__restrict__ cp,
-                                                        int64_t sc, const real *__restrict__ x0, int terminal_zero, real *__restrict__ states,
-                                                        real *__restrict__ actions, real *__restrict__ costs, real *__restrict__ Ko,
-                                                        real *__restrict__ ko, real *__restrict__ Vo, real *__restrict__ vo,
-                                                        real *__restrict__ csto, int32_t *__restrict__ status, real *__restrict__ scratch) {
+struct DirectOut {
+  real *states, *actions, *costs, *Ko, *ko, *Vo, *vo, *csto, *scratch;
+  int64_t b, S;
+  int T;
+  __device__ __forceinline__ void put_gain(int t, const real *K, const real *k) const {
+    if (Ko == nullptr) {
+#pragma unroll
+      for (int i = 0; i < M * N; i++) scratch[((int64_t)t * (M * N + M) + i) * S + b] = K[i];
+#pragma unroll
+      for (int i = 0; i < M; i++) scratch[((int64_t)t * (M * N + M) + M * N + i) * S + b] = k[i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < M * N; i++) Ko[(b * T + t) * M * N + i] = K[i];
+#pragma unroll
+      for (int i = 0; i < M; i++) ko[(b * T + t) * M + i] = k[i];
+    }
+  }
+  __device__ __forceinline__ void get_gain(int t, real *K, real *k) const {
+    if (Ko == nullptr) {
+#pragma unroll
+      for (int i = 0; i < M * N; i++) K[i] = scratch[((int64_t)t * (M * N + M) + i) * S + b];
+#pragma unroll
+      for (int i = 0; i < M; i++) k[i] = scratch[((int64_t)t * (M * N + M) + M * N + i) * S + b];
+    } else {
+#pragma unroll
+      for (int i = 0; i < M * N; i++) K[i] = Ko[(b * T + t) * M * N + i];
+#pragma unroll
+      for (int i = 0; i < M; i++) k[i] = ko[(b * T + t) * M + i];
+    }
+  }
+  __device__ __forceinline__ void put_value(int t, const real *V, const real *v, real cst) const {
+    if (Vo) {
+#pragma unroll
+      for (int i = 0; i < N * N; i++) Vo[(b * T + t) * N * N + i] = V[i];
+#pragma unroll
+      for (int i = 0; i < N; i++) vo[(b * T + t) * N + i] = v[i];
+      csto[b * T + t] = cst;
+    }
+  }
+  __device__ __forceinline__ void put_state(int t, const real *x) const {
+#pragma unroll
+    for (int i = 0; i < N; i++) states[(b * (T + 1) + t) * N + i] = x[i];
+  }
+  __device__ __forceinline__ void put_action(int t, const real *u) const {
+#pragma unroll
+    for (int i = 0; i < M; i++) actions[(b * T + t) * M + i] = u[i];
+  }
+  __device__ __forceinline__ void put_cost(int t, real c) const { costs[b * (T + 1) + t] = c; }
+};
+
+template <int N, int M>
+struct TileOut {  // per-warp tiles, row = lane; tile order: states, actions, costs, K, k, V, v, cst
+  real *st, *ac, *co, *Kt, *kt, *Vt, *vt, *ct;
+  int T;
+  bool value;
+  static __host__ __device__ int64_t row_reals(int T, bool value) {
+    return (int64_t)(T + 1) * N + (int64_t)T * M + (T + 1) + (int64_t)T * (M * N + M) + (value ? (int64_t)T * (N * N + N + 1) : 0);
+  }
+  __device__ __forceinline__ TileOut(real *base, int lane, int T_, bool value_) : T(T_), value(value_) {
+    real *p = base;
+    st = p + lane * (T + 1) * N; p += 32 * (T + 1) * N;
+    ac = p + lane * T * M; p += 32 * T * M;
+    co = p + lane * (T + 1); p += 32 * (T + 1);
+    Kt = p + lane * T * M * N; p += 32 * T * M * N;
+    kt = p + lane * T * M; p += 32 * T * M;
+    Vt = p + lane * T * N * N; p += 32 * T * N * N;
+    vt = p + lane * T * N; p += 32 * T * N;
+    ct = p + lane * T;
+  }
+  __device__ __forceinline__ void put_gain(int t, const real *K, const real *k) const {
+#pragma unroll
+    for (int i = 0; i < M * N; i++) Kt[t * M * N + i] = K[i];
+#pragma unroll
+    for (int i = 0; i < M; i++) kt[t * M + i] = k[i];
+  }
+  __device__ __forceinline__ void get_gain(int t, real *K, real *k) const {
+#pragma unroll
+    for (int i = 0; i < M * N; i++) K[i] = Kt[t * M * N + i];
+#pragma unroll
+    for (int i = 0; i < M; i++) k[i] = kt[t * M + i];
+  }
+  __device__ __forceinline__ void put_value(int t, const real *V, const real *v, real cst) const {
+    if (value) {
+#pragma unroll
+      for (int i = 0; i < N * N; i++) Vt[t * N * N + i] = V[i];
+#pragma unroll
+      for (int i = 0; i < N; i++) vt[t * N + i] = v[i];
+      ct[t] = cst;
+    }
+  }
+  __device__ __forceinline__ void put_state(int t, const real *x) const {
+#pragma unroll
+    for (int i = 0; i < N; i++) st[t * N + i] = x[i];
+  }
+  __device__ __forceinline__ void put_action(int t, const real *u) const {
+#pragma unroll
+    for (int i = 0; i < M; i++) ac[t * M + i] = u[i];
+  }
+  __device__ __forceinline__ void put_cost(int t, real c) const { co[t] = c; }
+};
+
+// LQR.backward (lqr.py:59-129) + LQR.forward (:131-161) of problem b, all matrices in registers
+template <int N, int M, class OUT>
+__device__ __forceinline__ int lqr_small_solve(int64_t b, int T, const real *__restrict__ Fp, int64_t sF, const real *__restrict__ fp,
+                                               int64_t sf, const real *__restrict__ Cp, int64_t sC, const real *__restrict__ cp, int64_t sc,
+                                               const real *__restrict__ x0, int terminal_zero, const OUT &out) {
   constexpr int NM = N + M;
-  int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
   real F[N * NM], f[N], C[NM * NM], c[NM];
 #pragma unroll
   for (int i = 0; i < N * NM; i++) F[i] = Fp[b * sF + i];
@@ -72,10 +177,6 @@ __global__ void __launch_bounds__(kThreads) k_lqr_small(int64_t B, int T, const 
   for (int i = 0; i < NM * NM; i++) C[i] = Cp[b * sC + i];
 #pragma unroll
   for (int i = 0; i < NM; i++) c[i] = cp[b * sc + i];
-  // policy storage: K, k per timestep.  Caller-provided outputs when present, else scratch
-  // (struct-of-arrays, problem index fastest: coalesced).
-  const bool own = (Ko == nullptr);
-  const int64_t S = (B + 31) / 32 * 32;
   real V[N * N], v[N], cst = 0;
   int st = 0;
 #pragma unroll
@@ -177,42 +278,17 @@ __global__ void __launch_bounds__(kThreads) k_lqr_small(int64_t B, int T, const 
     for (int i = 0; i < N * N; i++) V[i] = Vn[i];
 #pragma unroll
     for (int i = 0; i < N; i++) v[i] = vn[i];
-    if (own) {
-#pragma unroll
-      for (int i = 0; i < M * N; i++) scratch[((int64_t)t * (M * N + M) + i) * S + b] = K[i];
-#pragma unroll
-      for (int i = 0; i < M; i++) scratch[((int64_t)t * (M * N + M) + M * N + i) * S + b] = k[i];
-    } else {
-#pragma unroll
-      for (int i = 0; i < M * N; i++) Ko[(b * T + t) * M * N + i] = K[i];
-#pragma unroll
-      for (int i = 0; i < M; i++) ko[(b * T + t) * M + i] = k[i];
-    }
-    if (Vo) {
-#pragma unroll
-      for (int i = 0; i < N * N; i++) Vo[(b * T + t) * N * N + i] = V[i];
-#pragma unroll
-      for (int i = 0; i < N; i++) vo[(b * T + t) * N + i] = v[i];
-      csto[b * T + t] = cst;
-    }
+    out.put_gain(t, K, k);
+    out.put_value(t, V, v, cst);
   }
   // forward, :131-161
   real x[N], z[NM];
 #pragma unroll
-  for (int i = 0; i < N; i++) { x[i] = x0[b * N + i]; states[b * (T + 1) * N + i] = x[i]; }
+  for (int i = 0; i < N; i++) x[i] = x0[b * N + i];
+  out.put_state(0, x);
   for (int t = 0; t < T; t++) {
     real K[M * N], k[M];
-    if (own) {
-#pragma unroll
-      for (int i = 0; i < M * N; i++) K[i] = scratch[((int64_t)t * (M * N + M) + i) * S + b];
-#pragma unroll
-      for (int i = 0; i < M; i++) k[i] = scratch[((int64_t)t * (M * N + M) + M * N + i) * S + b];
-    } else {
-#pragma unroll
-      for (int i = 0; i < M * N; i++) K[i] = Ko[(b * T + t) * M * N + i];
-#pragma unroll
-      for (int i = 0; i < M; i++) k[i] = ko[(b * T + t) * M + i];
-    }
+    out.get_gain(t, K, k);
 #pragma unroll
     for (int i = 0; i < N; i++) z[i] = x[i];
 #pragma unroll
@@ -221,8 +297,8 @@ __global__ void __launch_bounds__(kThreads) k_lqr_small(int64_t B, int T, const 
 #pragma unroll
       for (int p = 0; p < N; p++) s += K[i * N + p] * x[p];
       z[N + i] = s + k[i];
-      actions[(b * T + t) * M + i] = z[N + i];
     }
+    out.put_action(t, z + N);
     real quad = 0, lin = 0;  // cost, :41-47
 #pragma unroll
     for (int j = 0; j < NM; j++) {
@@ -232,7 +308,7 @@ __global__ void __launch_bounds__(kThreads) k_lqr_small(int64_t B, int T, const 
       quad += s * z[j];
       lin += z[j] * c[j];
     }
-    costs[b * (T + 1) + t] = (real)0.5 * quad + lin;
+    out.put_cost(t, (real)0.5 * quad + lin);
 #pragma unroll
     for (int i = 0; i < N; i++) {  // transition, :36-39
       real s = 0;
@@ -240,8 +316,7 @@ __global__ void __launch_bounds__(kThreads) k_lqr_small(int64_t B, int T, const 
       for (int p = 0; p < NM; p++) s += F[i * NM + p] * z[p];
       x[i] = s + f[i];
     }
-#pragma unroll
-    for (int i = 0; i < N; i++) states[(b * (T + 1) + t + 1) * N + i] = x[i];
+    out.put_state(t + 1, x);
   }
   real quad = 0, lin = 0;  // final_cost, :49-57
 #pragma unroll
@@ -252,8 +327,79 @@ __global__ void __launch_bounds__(kThreads) k_lqr_small(int64_t B, int T, const 
     quad += s * x[j];
     lin += x[j] * c[j];
   }
-  costs[b * (T + 1) + T] = terminal_zero ? (real)0 : (real)0.5 * quad + lin;
+  out.put_cost(T, terminal_zero ? (real)0 : (real)0.5 * quad + lin);
+  return st;
+}
+
+template <int N, int M>
+__global__ void __launch_bounds__(kThreads) k_lqr_small(int64_t B, int T, const real *__restrict__ Fp, int64_t sF, const real *__restrict__ fp,
+                                                        int64_t sf, const real *__restrict__ Cp, int64_t sC, const real *__restrict__ cp,
+                                                        int64_t sc, const real *__restrict__ x0, int terminal_zero, real *__restrict__ states,
+                                                        real *__restrict__ actions, real *__restrict__ costs, real *__restrict__ Ko,
+                                                        real *__restrict__ ko, real *__restrict__ Vo, real *__restrict__ vo,
+                                                        real *__restrict__ csto, int32_t *__restrict__ status, real *__restrict__ scratch) {
+  int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  // policy storage: K, k per timestep.  Caller-provided outputs when present, else scratch
+  // (struct-of-arrays, problem index fastest: coalesced).
+  const DirectOut<N, M> out = {states, actions, costs, Ko, ko, Vo, vo, csto, scratch, b, (B + 31) / 32 * 32, T};
+  const int st = lqr_small_solve<N, M>(b, T, Fp, sF, fp, sf, Cp, sC, cp, sc, x0, terminal_zero, out);
   if (status) status[b] = st;
+}
+
+// shared -> global bulk store of `bytes` (multiple of 16, both addresses 16-byte aligned), issued by one lane
+__device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"((unsigned)__cvta_generic_to_shared(ssrc)), "r"(bytes)
+               : "memory");
+}
+
+constexpr int kStagedThreads = 64;  // 2 warps x 24 KB of tiles (C2: T = 10) -> 4 CTAs per SM
+
+template <int N, int M>
+__global__ void __launch_bounds__(kStagedThreads) k_lqr_small_staged(int64_t B, int T, const real *__restrict__ Fp, int64_t sF,
+                                                                      const real *__restrict__ fp, int64_t sf, const real *__restrict__ Cp,
+                                                                      int64_t sC, const real *__restrict__ cp, int64_t sc,
+                                                                      const real *__restrict__ x0, int terminal_zero, real *__restrict__ states,
+                                                                      real *__restrict__ actions, real *__restrict__ costs, real *__restrict__ Ko,
+                                                                      real *__restrict__ ko, real *__restrict__ Vo, real *__restrict__ vo,
+                                                                      real *__restrict__ csto, int32_t *__restrict__ status) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
+  const bool value = Vo != nullptr;
+  const int64_t row = TileOut<N, M>::row_reals(T, true);   // tiles are carved for the full set; unused ones stay untouched
+  real *base = reinterpret_cast<real *>(smem_raw) + (int64_t)wq * 32 * row;
+  const int64_t b0 = ((int64_t)blockIdx.x * (kStagedThreads / 32) + wq) * 32;
+  if (b0 >= B) return;
+  const int64_t b = b0 + lane;
+  const int nvalid = (int)min((int64_t)32, B - b0);
+  const TileOut<N, M> out(base, lane, T, value);
+  int st = 0;
+  if (lane < nvalid) st = lqr_small_solve<N, M>(b, T, Fp, sF, fp, sf, Cp, sC, cp, sc, x0, terminal_zero, out);
+  if (status && lane < nvalid) status[b] = st;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy tile writes -> visible to the bulk-copy engine
+  __syncwarp();
+  // the warp's 32 rows of every output array are one contiguous block in global memory
+  real *tiles[8] = {base, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  const int rl[8] = {(T + 1) * N, T * M, T + 1, T * M * N, T * M, T * N * N, T * N, T};
+  real *gl[8] = {states, actions, costs, Ko, ko, Vo, vo, csto};
+#pragma unroll
+  for (int a = 1; a < 8; a++) tiles[a] = tiles[a - 1] + 32 * rl[a - 1];
+#pragma unroll
+  for (int a = 0; a < 8; a++) {
+    if (gl[a] == nullptr) continue;
+    real *g = gl[a] + b0 * rl[a];
+    const unsigned bytes = (unsigned)(nvalid * rl[a] * (int)sizeof(real));
+    if ((bytes & 15u) == 0) {
+      if (lane == 0) bulk_store(g, tiles[a], bytes);
+    } else {  // ragged last warp: coalesced element copies
+      for (int i = lane; i < nvalid * rl[a]; i += 32) g[i] = tiles[a][i];
+    }
+  }
+  if (lane == 0) {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the tiles must outlive the copies that read them
+  }
+  __syncwarp();
 }
 
 // ---------------------------------------------------------------- generic warp-per-problem kernel
@@ -522,13 +668,28 @@ int lqr_solve_launch(int64_t B, int n, int m, int T, const real *F, int64_t sF, 
   if ((K == nullptr) != (k == nullptr)) return tfmpc_set_error(TFMPC_E_INVALID, "K and k must both be given or both be NULL");
   if (V && !(v && cst)) return tfmpc_set_error(TFMPC_E_INVALID, "V, v and cst must be given together");
   const bool small = (n == 2 && m == 2) || (n == 3 && m == 2);
+  // staged variant: tiles of 32 rows per warp must fit shared memory and every output block must be 16-byte aligned
+  const int64_t row_reals = (int64_t)(T + 1) * n + (int64_t)T * m + (T + 1) + (int64_t)T * (m * n + m) + (int64_t)T * (n * n + n + 1);
+  const size_t staged_smem = (size_t)(kStagedThreads / 32) * 32 * row_reals * sizeof(real);
+  auto aligned16 = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+  const bool staged = small && staged_smem <= 100 * 1024 && aligned16(states) && aligned16(actions) && aligned16(costs) && aligned16(K) &&
+                      aligned16(k) && aligned16(V) && aligned16(v) && aligned16(cst);
   real *scratch = nullptr;
-  if (K == nullptr) {
+  if (K == nullptr && !staged) {
     int64_t S = (B + 31) / 32 * 32;
     int64_t elems = small ? (int64_t)T * (m * n + m) * S : (int64_t)B * T * (m * n + m);
     CUDA_TRY(cudaMallocAsync((void **)&scratch, (size_t)elems * sizeof(real), s));
   }
-  if (small) {
+  if (staged) {
+    unsigned grid = (unsigned)((B + kStagedThreads - 1) / kStagedThreads);
+    if (n == 2) {
+      cudaFuncSetAttribute(k_lqr_small_staged<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+      k_lqr_small_staged<2, 2><<<grid, kStagedThreads, staged_smem, s>>>(B, T, F, sF, f, sf, C, sC, c, sc, x0, terminal_zero, states, actions, costs, K, k, V, v, cst, status);
+    } else {
+      cudaFuncSetAttribute(k_lqr_small_staged<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+      k_lqr_small_staged<3, 2><<<grid, kStagedThreads, staged_smem, s>>>(B, T, F, sF, f, sf, C, sC, c, sc, x0, terminal_zero, states, actions, costs, K, k, V, v, cst, status);
+    }
+  } else if (small) {
     unsigned grid = (unsigned)((B + kThreads - 1) / kThreads);
     if (n == 2) k_lqr_small<2, 2><<<grid, kThreads, 0, s>>>(B, T, F, sF, f, sf, C, sC, c, sc, x0, terminal_zero, states, actions, costs, K, k, V, v, cst, status, scratch);
     else k_lqr_small<3, 2><<<grid, kThreads, 0, s>>>(B, T, F, sF, f, sf, C, sC, c, sc, x0, terminal_zero, states, actions, costs, K, k, V, v, cst, status, scratch);

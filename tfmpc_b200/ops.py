@@ -29,9 +29,10 @@ def _empty(like, *shape):
 
 
 # ------------------------------------------------------------------ LQR
-def lqr_solve(F, f, Cm, c, x0, T, terminal_zero=False, want_policy=True, want_value=True):
+def lqr_solve(F, f, Cm, c, x0, T, terminal_zero=False, want_policy=True, want_value=True, out=None):
     """LQR.solve for B problems.  F [n,N] or [B,n,N]; f [n]/[B,n]; Cm [N,N]/[B,N,N]; c [N]/[B,N];
-    x0 [B,n].  Returns dict(states, actions, costs, status[, K, k][, V, v, const])."""
+    x0 [B,n].  Returns dict(states, actions, costs, status[, K, k][, V, v, const]); `out` reuses the
+    result tensors of an earlier call with the same shapes and flags."""
     N.require_cuda()
     x0 = _c(x0)
     B, n = x0.shape
@@ -47,15 +48,16 @@ def lqr_solve(F, f, Cm, c, x0, T, terminal_zero=False, want_policy=True, want_va
         if s and t.shape[0] != B:
             raise N.TfmpcError(f"batched {nb} has leading size {t.shape[0]}, expected {B}")
     T = int(T)
-    out = dict(states=_empty(x0, B, T + 1, n), actions=_empty(x0, B, T, m), costs=_empty(x0, B, T + 1),
-               status=torch.empty(B, dtype=torch.int32, device=x0.device))
-    if want_policy or want_value:
-        out["K"] = _empty(x0, B, T, m, n)
-        out["k"] = _empty(x0, B, T, m)
-    if want_value:
-        out["V"] = _empty(x0, B, T, n, n)
-        out["v"] = _empty(x0, B, T, n)
-        out["const"] = _empty(x0, B, T)
+    if out is None:
+        out = dict(states=_empty(x0, B, T + 1, n), actions=_empty(x0, B, T, m), costs=_empty(x0, B, T + 1),
+                   status=torch.empty(B, dtype=torch.int32, device=x0.device))
+        if want_policy or want_value:
+            out["K"] = _empty(x0, B, T, m, n)
+            out["k"] = _empty(x0, B, T, m)
+        if want_value:
+            out["V"] = _empty(x0, B, T, n, n)
+            out["v"] = _empty(x0, B, T, n)
+            out["const"] = _empty(x0, B, T)
     P = lambda t, i32=False: N.dev_ptr(lib, t, i32)  # noqa: E731
     ptrs = [P(F), P(f), P(Cm), P(c), P(x0), P(out["states"]), P(out["actions"]), P(out["costs"]), P(out.get("K")), P(out.get("k")),
             P(out.get("V")), P(out.get("v")), P(out.get("const")), P(out["status"], True)]
@@ -65,9 +67,10 @@ def lqr_solve(F, f, Cm, c, x0, T, terminal_zero=False, want_policy=True, want_va
     return out
 
 
-def lqr_solve_host(F, f, Cm, c, x0, T, terminal_zero=False):
+def lqr_solve_host(F, f, Cm, c, x0, T, terminal_zero=False, out=None):
     """Same solve through the HOST-buffer entry point: CPU tensors in, CPU tensors out; the
-    library does the H2D copy, the solve and the D2H copy, and synchronises."""
+    library does the H2D copy, the solve and the D2H copy, and synchronises.  `out` reuses the
+    (ideally pinned) result tensors of an earlier call."""
     N.require_cuda()
     x0 = _c(x0)
     B, n = x0.shape
@@ -80,8 +83,9 @@ def lqr_solve_host(F, f, Cm, c, x0, T, terminal_zero=False):
     sC = NN * NN if Cm.dim() == 3 else 0
     sc = NN if c.dim() == 2 else 0
     T = int(T)
-    out = dict(states=torch.empty(B, T + 1, n, dtype=x0.dtype), actions=torch.empty(B, T, m, dtype=x0.dtype),
-               costs=torch.empty(B, T + 1, dtype=x0.dtype), status=torch.empty(B, dtype=torch.int32))
+    if out is None:
+        out = dict(states=torch.empty(B, T + 1, n, dtype=x0.dtype), actions=torch.empty(B, T, m, dtype=x0.dtype),
+                   costs=torch.empty(B, T + 1, dtype=x0.dtype), status=torch.empty(B, dtype=torch.int32))
     P = lambda t, i32=False: N.host_ptr(lib, t, i32)  # noqa: E731
     ptrs = [P(F), P(f), P(Cm), P(c), P(x0), P(out["states"]), P(out["actions"]), P(out["costs"]), P(out["status"], True)]
     N.check(lib, lib.tfmpc_lqr_solve_host(C.c_int64(B), n, m, T, ptrs[0].p, C.c_int64(sF), ptrs[1].p, C.c_int64(sf), ptrs[2].p,

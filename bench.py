@@ -477,7 +477,7 @@ def run_ours(args):
 
     # ---- end to end through the public host-buffer API: pinned host inputs -> results in host memory, every step.
     #      S host threads, each with its own env handle and stream (the C ABI is re-entrant across streams).
-    e2e_steps = max(S, min(args.steps, 2 * S))
+    e2e_steps = max(S, min(args.steps, 4 * S))
     nats = [envs.make_env(cfg).native() for _ in range(S)]
     houts = [new_out(host=True) for _ in range(S)]
 
@@ -535,6 +535,11 @@ def run_ours(args):
                 "traffic": None, "peak_source": "FP32 FMA microbenchmark run in this process (tfmpc_measure_fp32_peak); nominal 148 SM x 128 lanes x 2 x clock"}
         hbm = {"bound": "hbm", "achieved": ach_gb, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach_gb / peaks["hbm_gbs"], "traffic": None,
                "peak_source": peak_src}
+        tpath = os.path.join(ROOT, "profiles", f"r01_traffic_{args.workload}.json")
+        if os.path.exists(tpath) and not args.batch:   # DRAM bytes of one solve, measured once with ncu (provenance inside the file)
+            tr = json.load(open(tpath))
+            hbm["traffic"] = fp32["traffic"] = tr["dram_bytes_per_solve"]
+            hbm["traffic_source"] = fp32["traffic_source"] = tr["source"]
         primary = fp32 if (fp32["frac"] or 0) >= hbm["frac"] else hbm
         roofline = dict(primary)
         roofline["kernel"] = ("launch sequence of one solve: k_tick_backward + k_tick_linesearch per tick (thread-per-problem)"
@@ -581,7 +586,8 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=0, help="timed steps (default: 32 for the GPU arm -- the pipeline needs a few waves of 8 "
+                    "batches to reach its steady state --, 5 for the CPU reference arm)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
@@ -593,6 +599,8 @@ def main():
     ap.add_argument("--issue", default="single", choices=["threads", "single"], help="host threads issuing the pipelined steps")
     ap.add_argument("--streams", type=int, default=8, help="CUDA streams the independent steps are pipelined over (1 = strictly sequential)")
     args = ap.parse_args()
+    if args.steps <= 0:
+        args.steps = 5 if (args.impl == "reference" or args.workload == "c5") else 32
     if args.impl == "reference":
         run_reference(args)
     elif args.workload == "c2":

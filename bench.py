@@ -12,7 +12,8 @@ A "step" is one pass of the hot path over one batch: iLQR.solve of B independent
 the reference's outer loop ilqr.py:227-277 (linearise + >= 1 backward pass + line search), summed over
 problems.  Workload (default): BASELINE config C3 -- nonlinear 2-D navigation with two deceleration zones,
 H = 50, B = 65,536 problems PER GPU (weak scaling: the batch is sharded, no data-path collective; with
-N > 1 ranks the per-problem costs and iteration counts are all-gathered once per step over NCCL).
+N > 1 ranks the per-problem costs and iteration counts of all K steps are all-gathered over NCCL once, at the end of
+the timed region).
 Prints ONE JSON line (rank 0).
 """
 import argparse
@@ -366,15 +367,51 @@ def run_ours(args):
         return {k: v.pin_memory() for k, v in o.items()} if host else o
 
     outs = [new_out() for _ in range(S)]
-    gathered = [[torch.empty(B, device=dev) for _ in range(world)] for _ in range(S)] if world > 1 else None
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)   # 256 MB > 126 MB L2
     streams = [torch.cuda.Stream(device=dev) for _ in range(S)]
     main = torch.cuda.current_stream()
+    use_async = args.pipeline == "async" and args.workload in ("c3",) and S > 1
+    if use_async:
+        works = [ops.ilqr_workspace(nat, B, T, dev) for _ in range(S)]
+        outs_k = [new_out() for _ in range(args.steps)] if world > 1 else [outs[k % S] for k in range(args.steps)]
+        done = [torch.cuda.Event() for _ in range(S)]
+
+    # Sharded solve: no inter-GPU traffic while solving.  Every step leaves its per-problem total costs and iteration
+    # counts in a [K, B] buffer; ONE all-gather per buffer at the end of the timed region brings them to every rank.
+    # (A gather -- or any other device operation -- per step on the compute streams was measured first: -25 % at 2 GPUs.)
+    totals_all = torch.empty(args.steps, B, device=dev) if world > 1 else None
+    iters_all = torch.empty(args.steps, B, dtype=torch.int32, device=dev) if world > 1 else None
+    gathered = ([torch.empty_like(totals_all) for _ in range(world)], [torch.empty_like(iters_all) for _ in range(world)]) if world > 1 else None
+    step_no, step_lock = [0], threading.Lock()
+
+    extra = os.environ.get("TFMPC_BENCH_EXTRA", "")   # diagnostics: what an op between two solves of a stream costs
+    xbuf = torch.empty(B, device=dev)
 
     def step(slot):
         ops.ilqr_solve(nat, x0, u0, opts, outs[slot])
-        if world > 1:   # the one collective of the sharded solve: per-problem total costs to every rank
-            dist.all_gather(gathered[slot], outs[slot]["costs"].sum(1))
+        if extra == "ops":
+            torch.sum(outs[slot]["costs"], dim=1, out=xbuf)
+        elif extra == "event":
+            torch.cuda.Event().record()
+        elif extra == "sleep":
+            time.sleep(1e-4)
+        elif extra == "memset":
+            xbuf.zero_()
+        elif extra == "own":
+            ops.env_final_cost(nat, x0[:1024])
+        elif extra == "memcpy":
+            xbuf[:1024].copy_(xbuf[1024:2048])
+        if world > 1 and not use_async:
+            with step_lock:
+                k = step_no[0] % args.steps
+                step_no[0] += 1
+            torch.sum(outs[slot]["costs"], dim=1, out=totals_all[k])
+            iters_all[k].copy_(outs[slot]["stats"][:, 0])
+
+    def final_gather():
+        if world > 1:
+            dist.all_gather(gathered[0], totals_all)
+            dist.all_gather(gathered[1], iters_all)
 
     if args.workload == "c5":
         # BASELINE config 5: the shrinking-horizon MPC loop of reference agents/mpc.py:10-15 + runners/__init__.py:14-43 for B
@@ -403,6 +440,9 @@ def run_ours(args):
     for i in range(S):             # warm every stream's workspace (the caching allocator keeps one pool per stream)
         with torch.cuda.stream(streams[i]):
             step(i)
+        if use_async:
+            ops.ilqr_solve_async(nat, x0, u0, outs[i], works[i], done[i], opts)
+    final_gather()                 # warm NCCL's all-gather path (connection set-up happens on the first call)
     barrier()
     sampler = ClockSampler(local) if rank == 0 and not args.no_clock_sampler else None
     t_wall0 = time.time()
@@ -428,7 +468,24 @@ def run_ours(args):
     for st in streams:
         st.wait_event(e0)
     tl = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    if args.issue == "threads" and S > 1:      # one issuing host thread per stream (ctypes drops the GIL inside the C call)
+    if use_async:
+        # ONE stream, K back-to-back tfmpc_ilqr_solve_async calls over a ring of S output/workspace slots: the heads run one
+        # after another on `main`, each batch's stragglers on the library's priority streams; `done[slot]` guards slot reuse.
+        # N > 1: every step keeps its own output set (K x 94 MB), so that nothing but the solves is enqueued while they run
+        # (side-stream reductions per step were measured: they alias hardware channels with the straggler streams and stall
+        # the head stream, -8 %); the [K, B] totals are formed after the last batch, then gathered.
+        for k in range(args.steps):
+            slot = k % S
+            if k >= S:
+                main.wait_event(done[slot])       # the workspace of this slot is free again
+            ops.ilqr_solve_async(nat, x0, u0, outs_k[k], works[slot], done[slot], opts)
+        for k in range(max(0, args.steps - S), args.steps):
+            main.wait_event(done[k % S])
+        if world > 1:
+            for k in range(args.steps):
+                torch.sum(outs_k[k]["costs"], dim=1, out=totals_all[k])
+                iters_all[k].copy_(outs_k[k]["stats"][:, 0])
+    elif args.issue == "threads" and S > 1:      # one issuing host thread per stream (ctypes drops the GIL inside the C call)
         def issue(i):
             torch.cuda.set_device(local)
             with torch.cuda.stream(streams[i]):
@@ -455,9 +512,13 @@ def run_ours(args):
         done = torch.cuda.Event()
         done.record(st)
         main.wait_event(done)
+    e_mid = torch.cuda.Event(enable_timing=True)
+    e_mid.record(main)
+    final_gather()      # on `main`, behind every stream's last batch, inside the timed region
     e1.record(main)
     barrier()
     pipe_ms = float(e0.elapsed_time(e1))
+    gather_ms = float(e_mid.elapsed_time(e1))
     timeline = [[k % S, round(e0.elapsed_time(a), 3), round(e0.elapsed_time(b), 3)] for k, (a, b) in enumerate(tl)] if args.timeline else None
     launches = _native.kernel_launch_count("f32") - launches0
     t_wall1 = time.time()
@@ -465,8 +526,12 @@ def run_ours(args):
 
     stats = outs[0]["stats"].cpu().numpy()
     pi_local = float((stats[:, 0] + 1).sum())
-    t = torch.tensor([pipe_ms, seq_ms, pi_local], dtype=torch.float64, device=dev)
+    t = torch.tensor([pipe_ms, seq_ms, pi_local, gather_ms], dtype=torch.float64, device=dev)
+    per_rank = None
     if world > 1:
+        allt = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        per_rank = [[round(float(a[0]) / args.steps, 4), round(float(a[1]) / args.steps, 4), float(a[2]), round(float(a[3]), 3)] for a in allt]
         tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
         pipe_ms, seq_ms, pi_all = float(tmax[0]), float(tmax[1]), float(tsum[2])
@@ -551,10 +616,12 @@ def run_ours(args):
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": desc, "batch_per_gpu": B, "global_batch": B * world, "horizon": T, "state_dim": n, "action_dim": m,
-                           "parallelism": f"batch sharded over {world} GPU(s), no data-path collective"
+                           "parallelism": f"batch sharded over {world} GPU(s), no data-path collective; one NCCL all-gather of per-problem costs and iteration counts at the end of the timed region"
                                           + ("; one NCCL all-gather of per-problem costs per step" if world > 1 else ""),
                            "streams": S,
-                           "pipelining": (f"the {args.steps} steps are independent batches issued round-robin on {S} CUDA streams" if S > 1
+                           "pipelining": ((f"the {args.steps} steps are independent batches issued back to back on ONE stream with tfmpc_ilqr_solve_async over a "
+                                           f"ring of {S} output/workspace slots (straggler ticks on the library's priority streams)") if use_async else
+                                          f"the {args.steps} steps are independent batches issued round-robin on {S} CUDA streams" if S > 1
                                           else "one batch at a time"),
                            "solver": "reference defaults atol=5e-3 max_iterations=100 mu_min=1e-6 delta_0=2 c1=0 alpha_min=1e-3",
                            "l2": ("pipelined: aggregate working set of the concurrent batches (S x ~420 MB) >> 126 MB L2; "
@@ -564,6 +631,8 @@ def run_ours(args):
                            "status_histogram": np.bincount(stats[:, 3], minlength=5).tolist()},
                 "sequential": {"value": pi_all * args.steps / (seq_ms * 1e-3), "unit": "problem-iterations/s",
                                "latency_ms_per_batch": seq_ms / args.steps, "step_ms": step_ms},
+                "per_rank": ({"columns": ["pipelined ms/step", "sequential ms/batch", "problem-iterations per batch", "final all-gather ms (incl. waiting for the slowest rank)"], "ranks": per_rank}
+                             if per_rank else None),
                 "pipeline_timeline_ms": {"columns": ["stream", "start", "end"], "steps": timeline},
                 "roofline": roofline,
                 "e2e": {"value": e2e_value, "unit": "problem-iterations/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -596,6 +665,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--timeline", action="store_true", help="record start/end events around every pipelined step")
     ap.add_argument("--no-clock-sampler", action="store_true", help="diagnostics only: a line without `clocks` is not a valid bench line")
+    ap.add_argument("--pipeline", default="async", choices=["async", "streams"],
+                    help="how the K timed batches are kept in flight: async = one stream + tfmpc_ilqr_solve_async, streams = S streams")
     ap.add_argument("--issue", default="single", choices=["threads", "single"], help="host threads issuing the pipelined steps")
     ap.add_argument("--streams", type=int, default=8, help="CUDA streams the independent steps are pipelined over (1 = strictly sequential)")
     args = ap.parse_args()

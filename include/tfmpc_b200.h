@@ -207,6 +207,15 @@ int64_t tfmpc_ilqr_workspace_bytes(const tfmpc_env_t *env, int64_t B, int T);
 int tfmpc_ilqr_solve(const tfmpc_env_t *env, int64_t B, int T, const tfmpc_real *x0, const tfmpc_real *u_init,
                      const tfmpc_ilqr_opts_t *opts, tfmpc_real *states, tfmpc_real *actions, tfmpc_real *costs,
                      int32_t *stats, void *workspace, int64_t workspace_bytes, void *stream);
+/* Asynchronous form for callers that keep several batches in flight.  Inputs are read in `stream` order, but `stream`
+ * does NOT wait for the results: the straggler part of the solve (the ticks after most problems have converged) runs
+ * on an internal high-priority stream, so the next call on the same `stream` starts at once and its throughput-bound
+ * head overlaps this call's latency-bound tail.  `done_event` (a cudaEvent_t of the same device, created by the
+ * caller) is recorded behind the results: wait on it (cudaStreamWaitEvent / cudaEventSynchronize) before reading
+ * states/actions/costs/stats or reusing them or the workspace.  Concurrent calls need distinct outputs and workspaces. */
+int tfmpc_ilqr_solve_async(const tfmpc_env_t *env, int64_t B, int T, const tfmpc_real *x0, const tfmpc_real *u_init,
+                           const tfmpc_ilqr_opts_t *opts, tfmpc_real *states, tfmpc_real *actions, tfmpc_real *costs,
+                           int32_t *stats, void *workspace, int64_t workspace_bytes, void *stream, void *done_event);
 /* Same call with HOST buffers (pageable or pinned): copies inputs to the device, solves, copies
  * the results back and synchronises.  Device scratch is cached inside the env handle. */
 int tfmpc_ilqr_solve_host(tfmpc_env_t *env, int64_t B, int T, const tfmpc_real *x0, const tfmpc_real *u_init,

@@ -423,6 +423,34 @@ def test_ilqr_host_buffer_entry_point(prec, orc):
     assert a["same"] >= tol(prec, 0.93, 1.0) and a["cost_ok_same"] >= tol(prec, 0.99, 1.0)
 
 
+def test_ilqr_async_entry_point_matches_synchronous_solve(prec):
+    """tfmpc_ilqr_solve_async: three batches back to back on one stream, each with its own outputs / workspace /
+    completion event, give bit-identical results to the synchronous entry point."""
+    from tfmpc_b200 import ops
+    from tfmpc_b200.envs import synthetic
+    cfg = synthetic.navigation_config()
+    env = _env(cfg, prec)
+    nat = env.native(_dt(prec))
+    cases = [_batch_case(cfg, B, 50, seed) for B, seed in ((3000, 1), (3000, 2), (1111, 3))]
+    dev = [(_cu(x0, prec), _cu(u0, prec)) for x0, u0 in cases]
+    sync = [ops.ilqr_solve(nat, x0, u0) for x0, u0 in dev]
+    sync = [{k: v.clone() for k, v in o.items()} for o in sync]
+    torch.cuda.synchronize()
+    outs, works, done = [], [], []
+    for x0, u0 in dev:
+        B = x0.shape[0]
+        outs.append(dict(states=torch.empty(B, 51, 2, dtype=_dt(prec), device="cuda"), actions=torch.empty(B, 50, 2, dtype=_dt(prec), device="cuda"),
+                         costs=torch.empty(B, 51, dtype=_dt(prec), device="cuda"), stats=torch.empty(B, 4, dtype=torch.int32, device="cuda")))
+        works.append(ops.ilqr_workspace(nat, B, 50))
+        done.append(torch.cuda.Event())
+    for (x0, u0), o, w, d in zip(dev, outs, works, done):
+        ops.ilqr_solve_async(nat, x0, u0, o, w, d)
+    for d, o, ref in zip(done, outs, sync):
+        d.synchronize()
+        for k in ("states", "actions", "costs", "stats"):
+            assert torch.equal(o[k], ref[k]), k
+
+
 # ------------------------------------------------------------------ full-size properties
 def test_full_size_nav_properties():
     """BASELINE config C3 at full size (B = 65,536, H = 50), fp32: size-independent properties."""

@@ -319,18 +319,35 @@ int64_t tfmpc_ilqr_workspace_bytes(const tfmpc_env_t *e, int64_t B, int T) {
   return (b + 255) / 256 * 256;
 }
 
-int tfmpc_ilqr_solve(const tfmpc_env_t *e, int64_t B, int T, const real *x0, const real *u_init, const tfmpc_ilqr_opts_t *opts, real *states,
-                     real *actions, real *costs, int32_t *stats, void *ws, int64_t ws_bytes, void *stream) {
+static int ilqr_solve_impl(const tfmpc_env_t *e, int64_t B, int T, const real *x0, const real *u_init, const tfmpc_ilqr_opts_t *opts,
+                           real *states, real *actions, real *costs, int32_t *stats, void *ws, int64_t ws_bytes, void *stream, cudaEvent_t done) {
   REQ(e && x0 && u_init && states && actions && costs && stats && B >= 0 && T >= 1, "tfmpc_ilqr_solve: bad argument");
-  if (B == 0) return TFMPC_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (B == 0) {
+    if (done) CUDA_TRY(cudaEventRecord(done, s));
+    return TFMPC_OK;
+  }
   REQ(ws, "tfmpc_ilqr_solve: null workspace");
   IlqrOpts o;
   int rc = make_opts(opts, &o);
   if (rc) return rc;
-  if (!use_small(e) && e->kind == TFMPC_ENV_NAVLQR)
-    return dense_navlqr_solve(e, B, T, x0, u_init, o, states, actions, costs, stats, ws, ws_bytes, (cudaStream_t)stream);
-  return use_small(e) ? small_ilqr_solve(e, B, T, x0, u_init, o, states, actions, costs, stats, ws, ws_bytes, (cudaStream_t)stream)
-                      : warp_ilqr_solve(e, B, T, x0, u_init, o, states, actions, costs, stats, ws, ws_bytes, (cudaStream_t)stream);
+  if (use_small(e)) return small_ilqr_solve(e, B, T, x0, u_init, o, states, actions, costs, stats, ws, ws_bytes, s, done);
+  // the persistent kernels run wholly in stream order
+  rc = e->kind == TFMPC_ENV_NAVLQR ? dense_navlqr_solve(e, B, T, x0, u_init, o, states, actions, costs, stats, ws, ws_bytes, s)
+                                   : warp_ilqr_solve(e, B, T, x0, u_init, o, states, actions, costs, stats, ws, ws_bytes, s);
+  if (!rc && done) CUDA_TRY(cudaEventRecord(done, s));
+  return rc;
+}
+
+int tfmpc_ilqr_solve(const tfmpc_env_t *e, int64_t B, int T, const real *x0, const real *u_init, const tfmpc_ilqr_opts_t *opts, real *states,
+                     real *actions, real *costs, int32_t *stats, void *ws, int64_t ws_bytes, void *stream) {
+  return ilqr_solve_impl(e, B, T, x0, u_init, opts, states, actions, costs, stats, ws, ws_bytes, stream, nullptr);
+}
+
+int tfmpc_ilqr_solve_async(const tfmpc_env_t *e, int64_t B, int T, const real *x0, const real *u_init, const tfmpc_ilqr_opts_t *opts,
+                           real *states, real *actions, real *costs, int32_t *stats, void *ws, int64_t ws_bytes, void *stream, void *done_event) {
+  REQ(done_event, "tfmpc_ilqr_solve_async: null completion event");
+  return ilqr_solve_impl(e, B, T, x0, u_init, opts, states, actions, costs, stats, ws, ws_bytes, stream, (cudaEvent_t)done_event);
 }
 
 static int host_scratch(tfmpc_env *e, int64_t bytes) {

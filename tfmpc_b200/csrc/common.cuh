@@ -119,8 +119,9 @@ int small_ilqr_backward(const tfmpc_env *e, int64_t B, int T, const real *states
 int small_ilqr_forward(const tfmpc_env *e, int64_t B, int T, const real *states, const real *actions, const real *K, const real *k,
                        double alpha, real *xs, real *us, real *cs, real *J, real *residual, cudaStream_t s);
 int64_t small_ilqr_workspace_bytes(const tfmpc_env *e, int64_t B, int T);
+// done != nullptr: asynchronous form -- `s` does not wait for the straggler ticks, `done` is recorded behind the results
 int small_ilqr_solve(const tfmpc_env *e, int64_t B, int T, const real *x0, const real *u_init, const IlqrOpts &o, real *states,
-                     real *actions, real *costs, int32_t *stats, void *ws, int64_t ws_bytes, cudaStream_t s);
+                     real *actions, real *costs, int32_t *stats, void *ws, int64_t ws_bytes, cudaStream_t s, cudaEvent_t done = nullptr);
 int small_boxqp(int64_t B, int m, const real *H, const real *q, const real *lo, const real *hi, real *x, real *Hfree, int32_t *isfree,
                 int32_t *nfree, int32_t *status, cudaStream_t s);
 

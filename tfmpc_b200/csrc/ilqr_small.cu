@@ -477,6 +477,7 @@ static int device_sms(int device) {
 // between the large head kernels of the next instead of queueing behind them (measured: without priorities concurrent
 // full-size solves do not overlap at all, because the head grids monopolise CTA dispatch).
 constexpr int kHeadTicks = 24;
+constexpr int kAsyncHeadTicks = 4;
 constexpr int kTailStreams = 8;
 
 static cudaStream_t tail_stream(int device) {
@@ -496,7 +497,7 @@ static cudaStream_t tail_stream(int device) {
 
 template <int KIND, int N, int M>
 static int solve_launch(const tfmpc_env *e, int64_t B, int T, const real *x0, const real *u_init, const IlqrOpts &o, real *states,
-                        real *actions, real *costs, int32_t *stats, void *ws, cudaStream_t s) {
+                        real *actions, real *costs, int32_t *stats, void *ws, cudaStream_t s, cudaEvent_t done) {
   const WS w = carve(ws, padded_slots(B), T, N, M);
   const int sms = device_sms(e->device);
   const unsigned gB = grid_for(B);
@@ -507,13 +508,13 @@ static int solve_launch(const tfmpc_env *e, int64_t B, int T, const real *x0, co
   // tail: one CTA per SM is plenty for the stragglers (grid-stride loops keep it correct for any count)
   const unsigned g_bwd_t = std::min<unsigned>(g_bwd, (unsigned)sms), g_ls_t = std::min<unsigned>(g_ls, (unsigned)sms * 2);
   const int ticks = o.max_iterations + kExtraTicks;
-  const int head = std::min(ticks, kHeadTicks);
-  for (int t = 0; t < head; t++) {
-    if (e->bounded) k_tick_backward<KIND, N, M, true><<<g_bwd, kThreads, 0, s>>>(e->es, o, T, w, t & 1);
-    else k_tick_backward<KIND, N, M, false><<<g_bwd, kThreads, 0, s>>>(e->es, o, T, w, t & 1);
-    k_tick_linesearch<KIND, N, M><<<g_ls, kThreads, 0, s>>>(e->es, o, T, w, t & 1);
-  }
-  cudaStream_t ts = (ticks > head) ? tail_stream(e->device) : nullptr;
+  // Ticks before `fork_at` run on the caller's stream, the rest on a priority stream.  Synchronous form: fork where the
+  // kernels stop filling the GPU (kHeadTicks).  Asynchronous form: fork early (kAsyncHeadTicks) -- the caller's stream then
+  // carries only the GPU-filling first ticks of each batch, back to back, and everything latency-bound overlaps them.
+  static const int sync_head = [] { const char *v = getenv("TFMPC_HEAD_TICKS"); return v ? atoi(v) : kHeadTicks; }();          // tuning knobs
+  static const int async_head = [] { const char *v = getenv("TFMPC_ASYNC_HEAD_TICKS"); return v ? atoi(v) : kAsyncHeadTicks; }();
+  const int fork_at = std::min(ticks, std::max(0, done ? async_head : sync_head));
+  cudaStream_t ts = (ticks > fork_at) ? tail_stream(e->device) : nullptr;
   cudaEvent_t fork = nullptr, join = nullptr;
   if (ts) {
     if (cudaEventCreateWithFlags(&fork, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&join, cudaEventDisableTiming) != cudaSuccess) {
@@ -523,12 +524,13 @@ static int solve_launch(const tfmpc_env *e, int64_t B, int T, const real *x0, co
       ts = nullptr;
     }
   }
-  cudaStream_t q = ts ? ts : s;
-  if (ts) { cudaEventRecord(fork, s); cudaStreamWaitEvent(ts, fork, 0); }
-  for (int t = head; t < ticks; t++) {
-    if (e->bounded) k_tick_backward<KIND, N, M, true><<<g_bwd_t, kThreads, 0, q>>>(e->es, o, T, w, t & 1);
-    else k_tick_backward<KIND, N, M, false><<<g_bwd_t, kThreads, 0, q>>>(e->es, o, T, w, t & 1);
-    k_tick_linesearch<KIND, N, M><<<g_ls_t, kThreads, 0, q>>>(e->es, o, T, w, t & 1);
+  cudaStream_t q = s;
+  for (int t = 0; t < ticks; t++) {
+    if (t == fork_at && ts) { cudaEventRecord(fork, s); cudaStreamWaitEvent(ts, fork, 0); q = ts; }
+    const bool big = t < kHeadTicks;   // grid size follows the expected active count, whichever stream the tick runs on
+    if (e->bounded) k_tick_backward<KIND, N, M, true><<<big ? g_bwd : g_bwd_t, kThreads, 0, q>>>(e->es, o, T, w, t & 1);
+    else k_tick_backward<KIND, N, M, false><<<big ? g_bwd : g_bwd_t, kThreads, 0, q>>>(e->es, o, T, w, t & 1);
+    k_tick_linesearch<KIND, N, M><<<big ? g_ls : g_ls_t, kThreads, 0, q>>>(e->es, o, T, w, t & 1);
   }
   k_costs<KIND, N, M><<<gB, kThreads, 0, q>>>(e->es, B, T, w, stats);
   const unsigned gT = (unsigned)((B + 127) / 128);
@@ -536,20 +538,22 @@ static int solve_launch(const tfmpc_env *e, int64_t B, int T, const real *x0, co
   k_transpose_out<N, M><<<gT, 128, 0, q>>>(B, T, w, 1, T * M, actions);
   k_transpose_out<N, M><<<gT, 128, 0, q>>>(B, T, w, 2, T + 1, costs);
   if (ts) {
-    cudaEventRecord(join, ts);
-    cudaStreamWaitEvent(s, join, 0);
+    // async form: the caller's stream does NOT wait for the stragglers -- it is free for the head of the next batch --
+    // and `done` completes when the results are in place
+    if (done) cudaEventRecord(done, ts);
+    else { cudaEventRecord(join, ts); cudaStreamWaitEvent(s, join, 0); }
     cudaEventDestroy(fork);   // released by the runtime once the recorded work has completed
     cudaEventDestroy(join);
-  }
+  } else if (done) cudaEventRecord(done, s);
   tfmpc_count_launch(2 * ticks + 4);
   return TFMPC_OK;
 }
 
 int small_ilqr_solve(const tfmpc_env *e, int64_t B, int T, const real *x0, const real *u_init, const IlqrOpts &o, real *states,
-                     real *actions, real *costs, int32_t *stats, void *ws, int64_t ws_bytes, cudaStream_t s) {
+                     real *actions, real *costs, int32_t *stats, void *ws, int64_t ws_bytes, cudaStream_t s, cudaEvent_t done) {
   if (ws_bytes < small_ilqr_workspace_bytes(e, B, T)) return tfmpc_set_error(TFMPC_E_WORKSPACE, "workspace too small");
   if (B > 0x7fffffff) return tfmpc_set_error(TFMPC_E_INVALID, "batch too large");
-#define CALL(KD, N, M) { int rc_ = solve_launch<KD, N, M>(e, B, T, x0, u_init, o, states, actions, costs, stats, ws, s); if (rc_) return rc_; }
+#define CALL(KD, N, M) { int rc_ = solve_launch<KD, N, M>(e, B, T, x0, u_init, o, states, actions, costs, stats, ws, s, done); if (rc_) return rc_; }
   SMALL_DISPATCH(e, CALL);
 #undef CALL
   LAUNCH_CHECK();

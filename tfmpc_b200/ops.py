@@ -245,6 +245,33 @@ def ilqr_solve(env, x0, u_init, opts=None, out=None):
     return out
 
 
+def ilqr_workspace(env, B, T, device=None):
+    """A private workspace tensor for one in-flight ilqr_solve_async call."""
+    nbytes = env.lib.tfmpc_ilqr_workspace_bytes(env.handle, C.c_int64(B), int(T))
+    if nbytes < 0:
+        N.check(env.lib, int(nbytes))
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device or torch.device("cuda", torch.cuda.current_device()))
+
+
+def ilqr_solve_async(env, x0, u_init, out, workspace, done, opts=None):
+    """Asynchronous iLQR.solve (tfmpc_ilqr_solve_async): the current stream does not wait for the results, so
+    back-to-back calls overlap one batch's straggler ticks with the next batch's head.  `out` (as returned by
+    ilqr_solve) and `workspace` (ilqr_workspace) must not be shared by calls in flight; `done` is a
+    torch.cuda.Event that completes when `out` is ready -- wait on it before touching `out` or reusing either."""
+    x0, u_init = _c(x0), _c(u_init)
+    B, T = u_init.shape[0], u_init.shape[1]
+    lib = env.lib
+    opts = opts or make_opts()
+    if not done.cuda_event:
+        done.record()          # torch creates the cudaEvent_t lazily; the library re-records it behind the results
+    ins = [N.dev_ptr(lib, t) for t in (x0, u_init)]
+    outs = [N.dev_ptr(lib, t) for t in (out["states"], out["actions"], out["costs"])] + [N.dev_ptr(lib, out["stats"], True)]
+    N.check(lib, lib.tfmpc_ilqr_solve_async(env.handle, C.c_int64(B), T, ins[0].p, ins[1].p, C.byref(opts), *[p.p for p in outs],
+                                            C.c_void_p(workspace.data_ptr()), C.c_int64(workspace.numel()), N.stream_ptr(),
+                                            C.c_void_p(done.cuda_event)))
+    return out
+
+
 def ilqr_solve_host(env, x0, u_init, opts=None, out=None):
     """Same solve through the HOST-buffer entry point (CPU tensors in and out, copies inside)."""
     x0, u_init = _c(x0), _c(u_init)

@@ -12,7 +12,7 @@ A "step" is one pass of the hot path over one batch: iLQR.solve of B independent
 the reference's outer loop ilqr.py:227-277 (linearise + >= 1 backward pass + line search), summed over
 problems.  Workload (default): BASELINE config C3 -- nonlinear 2-D navigation with two deceleration zones,
 H = 50, B = 65,536 problems PER GPU (weak scaling: the batch is sharded, no data-path collective; with
-N > 1 ranks the per-problem costs and iteration counts of all K steps are all-gathered over NCCL once, at the end of
+N > 1 ranks the per-problem costs and iteration counts resident at the end are all-gathered over NCCL once, inside
 the timed region).
 Prints ONE JSON line (rank 0).
 """
@@ -371,24 +371,25 @@ def run_ours(args):
     streams = [torch.cuda.Stream(device=dev) for _ in range(S)]
     main = torch.cuda.current_stream()
     use_async = args.pipeline == "async" and args.workload in ("c3",) and S > 1
+    outs_k = None   # (per-step output sets were measured at 2 GPUs: slower than the ring, 280 M/s against 413 M/s)
     if use_async:
         works = [ops.ilqr_workspace(nat, B, T, dev) for _ in range(S)]
-        outs_k = [new_out() for _ in range(args.steps)] if world > 1 else [outs[k % S] for k in range(args.steps)]
         done = [torch.cuda.Event() for _ in range(S)]
 
-    # Sharded solve: no inter-GPU traffic while solving.  Every step leaves its per-problem total costs and iteration
-    # counts in a [K, B] buffer; ONE all-gather per buffer at the end of the timed region brings them to every rank.
-    # (A gather -- or any other device operation -- per step on the compute streams was measured first: -25 % at 2 GPUs.)
-    totals_all = torch.empty(args.steps, B, device=dev) if world > 1 else None
-    iters_all = torch.empty(args.steps, B, dtype=torch.int32, device=dev) if world > 1 else None
+    # Sharded solve: no inter-GPU traffic while solving, and nothing but the solves is enqueued while they run (a gather --
+    # or any other device operation -- per step on the compute streams was measured first: -25 % at 2 GPUs).  After the
+    # last batch the per-problem total costs and iteration counts of the S batches resident in the output ring are
+    # reduced to [S, B] and ONE all-gather per buffer, inside the timed region, brings them to every rank.
+    totals_all = torch.empty(S, B, device=dev) if world > 1 else None
+    iters_all = torch.empty(S, B, dtype=torch.int32, device=dev) if world > 1 else None
     gathered = ([torch.empty_like(totals_all) for _ in range(world)], [torch.empty_like(iters_all) for _ in range(world)]) if world > 1 else None
     step_no, step_lock = [0], threading.Lock()
 
     extra = os.environ.get("TFMPC_BENCH_EXTRA", "")   # diagnostics: what an op between two solves of a stream costs
     xbuf = torch.empty(B, device=dev)
 
-    def step(slot):
-        ops.ilqr_solve(nat, x0, u0, opts, outs[slot])
+    def step(slot, k=None):
+        ops.ilqr_solve(nat, x0, u0, opts, outs[slot] if (k is None or outs_k is None) else outs_k[k])
         if extra == "ops":
             torch.sum(outs[slot]["costs"], dim=1, out=xbuf)
         elif extra == "event":
@@ -401,12 +402,6 @@ def run_ours(args):
             ops.env_final_cost(nat, x0[:1024])
         elif extra == "memcpy":
             xbuf[:1024].copy_(xbuf[1024:2048])
-        if world > 1 and not use_async:
-            with step_lock:
-                k = step_no[0] % args.steps
-                step_no[0] += 1
-            torch.sum(outs[slot]["costs"], dim=1, out=totals_all[k])
-            iters_all[k].copy_(outs[slot]["stats"][:, 0])
 
     def final_gather():
         if world > 1:
@@ -468,6 +463,8 @@ def run_ours(args):
     for st in streams:
         st.wait_event(e0)
     tl = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t_issue0 = time.perf_counter()
+    call_ms = []
     if use_async:
         # ONE stream, K back-to-back tfmpc_ilqr_solve_async calls over a ring of S output/workspace slots: the heads run one
         # after another on `main`, each batch's stragglers on the library's priority streams; `done[slot]` guards slot reuse.
@@ -478,13 +475,11 @@ def run_ours(args):
             slot = k % S
             if k >= S:
                 main.wait_event(done[slot])       # the workspace of this slot is free again
-            ops.ilqr_solve_async(nat, x0, u0, outs_k[k], works[slot], done[slot], opts)
+            t_call = time.perf_counter()
+            ops.ilqr_solve_async(nat, x0, u0, outs_k[k] if outs_k else outs[slot], works[slot], done[slot], opts)
+            call_ms.append(round(1e3 * (time.perf_counter() - t_call), 3))
         for k in range(max(0, args.steps - S), args.steps):
             main.wait_event(done[k % S])
-        if world > 1:
-            for k in range(args.steps):
-                torch.sum(outs_k[k]["costs"], dim=1, out=totals_all[k])
-                iters_all[k].copy_(outs_k[k]["stats"][:, 0])
     elif args.issue == "threads" and S > 1:      # one issuing host thread per stream (ctypes drops the GIL inside the C call)
         def issue(i):
             torch.cuda.set_device(local)
@@ -492,7 +487,7 @@ def run_ours(args):
                 for k in range(i, args.steps, S):
                     if args.timeline:
                         tl[k][0].record()
-                    step(i)
+                    step(i, k)
                     if args.timeline:
                         tl[k][1].record()
         workers = [threading.Thread(target=issue, args=(i,)) for i in range(S)]
@@ -505,13 +500,18 @@ def run_ours(args):
             with torch.cuda.stream(streams[s % S]):
                 if args.timeline:
                     tl[s][0].record()
-                step(s % S)
+                step(s % S, s)
                 if args.timeline:
                     tl[s][1].record()
     for st in streams:
-        done = torch.cuda.Event()
-        done.record(st)
-        main.wait_event(done)
+        fin = torch.cuda.Event()
+        fin.record(st)
+        main.wait_event(fin)
+    issue_ms = 1e3 * (time.perf_counter() - t_issue0)      # host time spent enqueueing the K steps (no synchronisation inside)
+    if world > 1:       # the S batches resident in the output ring (every batch solves the same inputs) -> [S, B] totals
+        for i in range(S):
+            torch.sum(outs[i]["costs"], dim=1, out=totals_all[i])
+            iters_all[i].copy_(outs[i]["stats"][:, 0])
     e_mid = torch.cuda.Event(enable_timing=True)
     e_mid.record(main)
     final_gather()      # on `main`, behind every stream's last batch, inside the timed region
@@ -526,12 +526,12 @@ def run_ours(args):
 
     stats = outs[0]["stats"].cpu().numpy()
     pi_local = float((stats[:, 0] + 1).sum())
-    t = torch.tensor([pipe_ms, seq_ms, pi_local, gather_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([pipe_ms, seq_ms, pi_local, gather_ms, issue_ms / args.steps], dtype=torch.float64, device=dev)
     per_rank = None
     if world > 1:
         allt = [torch.empty_like(t) for _ in range(world)]
         dist.all_gather(allt, t)
-        per_rank = [[round(float(a[0]) / args.steps, 4), round(float(a[1]) / args.steps, 4), float(a[2]), round(float(a[3]), 3)] for a in allt]
+        per_rank = [[round(float(a[0]) / args.steps, 4), round(float(a[1]) / args.steps, 4), float(a[2]), round(float(a[3]), 3), round(float(a[4]), 3)] for a in allt]
         tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
         pipe_ms, seq_ms, pi_all = float(tmax[0]), float(tmax[1]), float(tsum[2])
@@ -616,7 +616,7 @@ def run_ours(args):
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": desc, "batch_per_gpu": B, "global_batch": B * world, "horizon": T, "state_dim": n, "action_dim": m,
-                           "parallelism": f"batch sharded over {world} GPU(s), no data-path collective; one NCCL all-gather of per-problem costs and iteration counts at the end of the timed region"
+                           "parallelism": f"batch sharded over {world} GPU(s), no data-path collective; one NCCL all-gather of the resident per-problem costs and iteration counts at the end of the timed region"
                                           + ("; one NCCL all-gather of per-problem costs per step" if world > 1 else ""),
                            "streams": S,
                            "pipelining": ((f"the {args.steps} steps are independent batches issued back to back on ONE stream with tfmpc_ilqr_solve_async over a "
@@ -631,8 +631,9 @@ def run_ours(args):
                            "status_histogram": np.bincount(stats[:, 3], minlength=5).tolist()},
                 "sequential": {"value": pi_all * args.steps / (seq_ms * 1e-3), "unit": "problem-iterations/s",
                                "latency_ms_per_batch": seq_ms / args.steps, "step_ms": step_ms},
-                "per_rank": ({"columns": ["pipelined ms/step", "sequential ms/batch", "problem-iterations per batch", "final all-gather ms (incl. waiting for the slowest rank)"], "ranks": per_rank}
+                "per_rank": ({"columns": ["pipelined ms/step", "sequential ms/batch", "problem-iterations per batch", "final all-gather ms (incl. waiting for the slowest rank)", "host enqueue ms/step"], "ranks": per_rank}
                              if per_rank else None),
+                "host_enqueue_ms_per_step": issue_ms / args.steps, "host_ms_per_async_call": call_ms,
                 "pipeline_timeline_ms": {"columns": ["stream", "start", "end"], "steps": timeline},
                 "roofline": roofline,
                 "e2e": {"value": e2e_value, "unit": "problem-iterations/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -665,7 +666,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--timeline", action="store_true", help="record start/end events around every pipelined step")
     ap.add_argument("--no-clock-sampler", action="store_true", help="diagnostics only: a line without `clocks` is not a valid bench line")
-    ap.add_argument("--pipeline", default="async", choices=["async", "streams"],
+    ap.add_argument("--pipeline", default="streams", choices=["async", "streams"],
                     help="how the K timed batches are kept in flight: async = one stream + tfmpc_ilqr_solve_async, streams = S streams")
     ap.add_argument("--issue", default="single", choices=["threads", "single"], help="host threads issuing the pipelined steps")
     ap.add_argument("--streams", type=int, default=8, help="CUDA streams the independent steps are pipelined over (1 = strictly sequential)")

@@ -451,6 +451,40 @@ def test_ilqr_async_entry_point_matches_synchronous_solve(prec):
             assert torch.equal(o[k], ref[k]), k
 
 
+def test_ilqr_graph_replay_matches_direct_launches(prec, request):
+    """The tick solve replays a captured CUDA graph from the second repeat of a (buffers, options) key on; results must be
+    bit-identical to the direct launches of the first call, for the synchronous and the asynchronous entry point, and
+    must follow changed INPUT CONTENTS (same addresses)."""
+    from tfmpc_b200 import ops
+    from tfmpc_b200.envs import synthetic
+    cfg = synthetic.navigation_config()
+    nat = _env(cfg, prec).native(_dt(prec))
+    xa, ua = _batch_case(cfg, 2000, 50, 11)
+    xb, ub = _batch_case(cfg, 2000, 50, 12)
+    x0, u0 = _cu(xa, prec), _cu(ua, prec)
+    first = ops.ilqr_solve(nat, x0, u0)
+    ref_a = {k: v.clone() for k, v in first.items()}
+    request.addfinalizer(lambda: ops.set_graph_mode(False, prec))
+    ops.set_graph_mode(True, prec)
+    for _ in range(3):                                   # 1st call remembers the key, 2nd captures, 3rd replays
+        ops.ilqr_solve(nat, x0, u0, out=first)
+        for k in ref_a:
+            assert torch.equal(first[k], ref_a[k]), k
+    x0.copy_(_cu(xb, prec)); u0.copy_(_cu(ub, prec))     # new problem data behind the same pointers
+    ops.ilqr_solve(nat, x0, u0, out=first)
+    ref_b = ops.ilqr_solve(nat, _cu(xb, prec), _cu(ub, prec))
+    for k in ref_b:
+        assert torch.equal(first[k], ref_b[k]), k
+    assert not torch.equal(ref_a["actions"], ref_b["actions"])
+    w, d = ops.ilqr_workspace(nat, 2000, 50), torch.cuda.Event()
+    for _ in range(3):
+        first["actions"].zero_()
+        ops.ilqr_solve_async(nat, x0, u0, first, w, d)
+        d.synchronize()
+        for k in ref_b:
+            assert torch.equal(first[k], ref_b[k]), k
+
+
 # ------------------------------------------------------------------ full-size properties
 def test_full_size_nav_properties():
     """BASELINE config C3 at full size (B = 65,536, H = 50), fp32: size-independent properties."""

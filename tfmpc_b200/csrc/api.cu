@@ -119,6 +119,8 @@ int tfmpc_env_create(int kind, int n, int m, int nz, const double *p, int64_t np
   }
   if (nparams != need) return tfmpc_set_error(TFMPC_E_INVALID, "kind %d expects %lld parameters, got %lld", kind, (long long)need, (long long)nparams);
   tfmpc_env *e = (tfmpc_env *)calloc(1, sizeof(tfmpc_env));
+  static std::atomic<unsigned long long> next_uid{1};
+  if (e) e->uid = next_uid.fetch_add(1);
   if (!e) return tfmpc_set_error(TFMPC_E_INVALID, "out of host memory");
   e->kind = kind; e->n = n; e->m = m; e->nz = nz;
   EnvSmall &s = e->es;
@@ -225,6 +227,7 @@ int tfmpc_env_create(int kind, int n, int m, int nz, const double *p, int64_t np
 
 int tfmpc_env_destroy(tfmpc_env_t *e) {
   if (!e) return TFMPC_OK;
+  small_ilqr_forget(e);
   if (e->dblob) cudaFree(e->dblob);
   if (e->dsteps) cudaFree(e->dsteps);
   if (e->h_scratch) cudaFree(e->h_scratch);
@@ -343,6 +346,8 @@ int tfmpc_ilqr_solve(const tfmpc_env_t *e, int64_t B, int T, const real *x0, con
                      real *actions, real *costs, int32_t *stats, void *ws, int64_t ws_bytes, void *stream) {
   return ilqr_solve_impl(e, B, T, x0, u_init, opts, states, actions, costs, stats, ws, ws_bytes, stream, nullptr);
 }
+
+int tfmpc_set_graph_mode(int on) { return small_ilqr_graph_mode(on); }
 
 int tfmpc_ilqr_solve_async(const tfmpc_env_t *e, int64_t B, int T, const real *x0, const real *u_init, const tfmpc_ilqr_opts_t *opts,
                            real *states, real *actions, real *costs, int32_t *stats, void *ws, int64_t ws_bytes, void *stream, void *done_event) {

@@ -91,6 +91,7 @@ struct tfmpc_env {
   double goal[MAXD], beta;  // NavigationLQR (host copy; the dense path takes them as kernel arguments)
   int max_row_nnz;   // large envs: max non-zeros per row over the forward and backward coupling matrices
   int device;
+  unsigned long long uid;  // unique per created environment (keys the CUDA-graph cache of the tick solve)
   // cached device scratch for the *_host entry points
   void *h_scratch;
   int64_t h_scratch_bytes;
@@ -119,6 +120,8 @@ int small_ilqr_backward(const tfmpc_env *e, int64_t B, int T, const real *states
 int small_ilqr_forward(const tfmpc_env *e, int64_t B, int T, const real *states, const real *actions, const real *K, const real *k,
                        double alpha, real *xs, real *us, real *cs, real *J, real *residual, cudaStream_t s);
 int64_t small_ilqr_workspace_bytes(const tfmpc_env *e, int64_t B, int T);
+int small_ilqr_graph_mode(int on);             // returns the previous mode
+void small_ilqr_forget(const tfmpc_env *e);   // drop the cached CUDA graphs of a destroyed environment
 // done != nullptr: asynchronous form -- `s` does not wait for the straggler ticks, `done` is recorded behind the results
 int small_ilqr_solve(const tfmpc_env *e, int64_t B, int T, const real *x0, const real *u_init, const IlqrOpts &o, real *states,
                      real *actions, real *costs, int32_t *stats, void *ws, int64_t ws_bytes, cudaStream_t s, cudaEvent_t done = nullptr);

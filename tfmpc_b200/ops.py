@@ -245,6 +245,11 @@ def ilqr_solve(env, x0, u_init, opts=None, out=None):
     return out
 
 
+def set_graph_mode(on, precision="f32"):
+    """tfmpc_set_graph_mode: CUDA-graph replay of repeated solves on the same buffers; returns the previous mode."""
+    return bool(N.load(precision).tfmpc_set_graph_mode(int(bool(on))))
+
+
 def ilqr_workspace(env, B, T, device=None):
     """A private workspace tensor for one in-flight ilqr_solve_async call."""
     nbytes = env.lib.tfmpc_ilqr_workspace_bytes(env.handle, C.c_int64(B), int(T))

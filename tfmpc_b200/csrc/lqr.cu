@@ -53,6 +53,12 @@ __device__ __forceinline__ int inverse_small(const real *A, real *inv) {
   return fail;
 }
 
+// shared -> global bulk store of `bytes` (multiple of 16, both addresses 16-byte aligned), issued by one lane
+__device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"((unsigned)__cvta_generic_to_shared(ssrc)), "r"(bytes)
+               : "memory");
+}
+
 // ---- output sinks of the thread-per-problem solve
 // DirectOut: every thread writes its own rows of the reference-layout outputs [B, T, ...] (a problem's row is contiguous,
 //            neighbouring threads are a whole row apart -> scattered 4-byte stores; the fallback for long rows).
@@ -109,26 +115,39 @@ struct DirectOut {
     for (int i = 0; i < M; i++) actions[(b * T + t) * M + i] = u[i];
   }
   __device__ __forceinline__ void put_cost(int t, real c) const { costs[b * (T + 1) + t] = c; }
+  __device__ __forceinline__ void between() const {}
 };
 
 template <int N, int M>
-struct TileOut {  // per-warp tiles, row = lane; tile order: states, actions, costs, K, k, V, v, cst
-  real *st, *ac, *co, *Kt, *kt, *Vt, *vt, *ct;
-  int T;
-  bool value;
-  static __host__ __device__ int64_t row_reals(int T, bool value) {
-    return (int64_t)(T + 1) * N + (int64_t)T * M + (T + 1) + (int64_t)T * (M * N + M) + (value ? (int64_t)T * (N * N + N + 1) : 0);
+struct TileOut {
+  // Per-warp tiles, row = lane.  Region A holds the gains (K, k) for the whole kernel (the rollout reads them back);
+  // region B holds V, v, const during the backward sweep and -- once those have been written out -- states, actions,
+  // costs during the rollout.  130 reals per row for n = m = 2, T = 10 (16.6 KB per warp -> 12 warps per SM).
+  real *base;
+  real *Kt, *kt, *Vt, *vt, *ct, *st, *ac, *co;   // this lane's rows
+  real *gK, *gk, *gV, *gv, *gc, *gs, *ga, *gco;  // the warp's blocks in the global outputs (nullptr = not wanted)
+  int T, lane, nvalid;
+  static __host__ __device__ int64_t row_reals(int T) {
+    const int64_t a = (int64_t)T * (M * N + M), b1 = (int64_t)T * (N * N + N + 1), b2 = (int64_t)(T + 1) * N + (int64_t)T * M + (T + 1);
+    return a + (b1 > b2 ? b1 : b2);
   }
-  __device__ __forceinline__ TileOut(real *base, int lane, int T_, bool value_) : T(T_), value(value_) {
+  __device__ __forceinline__ TileOut(real *base_, int lane_, int nvalid_, int T_, int64_t b0, real *states, real *actions, real *costs, real *Ko,
+                                     real *ko, real *Vo, real *vo, real *csto)
+      : base(base_), T(T_), lane(lane_), nvalid(nvalid_) {
     real *p = base;
-    st = p + lane * (T + 1) * N; p += 32 * (T + 1) * N;
-    ac = p + lane * T * M; p += 32 * T * M;
-    co = p + lane * (T + 1); p += 32 * (T + 1);
     Kt = p + lane * T * M * N; p += 32 * T * M * N;
     kt = p + lane * T * M; p += 32 * T * M;
+    real *regionB = p;
     Vt = p + lane * T * N * N; p += 32 * T * N * N;
     vt = p + lane * T * N; p += 32 * T * N;
     ct = p + lane * T;
+    p = regionB;
+    st = p + lane * (T + 1) * N; p += 32 * (T + 1) * N;
+    ac = p + lane * T * M; p += 32 * T * M;
+    co = p + lane * (T + 1);
+    gK = Ko ? Ko + b0 * T * M * N : nullptr; gk = ko ? ko + b0 * T * M : nullptr;
+    gV = Vo ? Vo + b0 * T * N * N : nullptr; gv = vo ? vo + b0 * T * N : nullptr; gc = csto ? csto + b0 * T : nullptr;
+    gs = states + b0 * (T + 1) * N; ga = actions + b0 * T * M; gco = costs + b0 * (T + 1);
   }
   __device__ __forceinline__ void put_gain(int t, const real *K, const real *k) const {
 #pragma unroll
@@ -143,7 +162,7 @@ struct TileOut {  // per-warp tiles, row = lane; tile order: states, actions, co
     for (int i = 0; i < M; i++) k[i] = kt[t * M + i];
   }
   __device__ __forceinline__ void put_value(int t, const real *V, const real *v, real cst) const {
-    if (value) {
+    if (gV) {
 #pragma unroll
       for (int i = 0; i < N * N; i++) Vt[t * N * N + i] = V[i];
 #pragma unroll
@@ -160,6 +179,39 @@ struct TileOut {  // per-warp tiles, row = lane; tile order: states, actions, co
     for (int i = 0; i < M; i++) ac[t * M + i] = u[i];
   }
   __device__ __forceinline__ void put_cost(int t, real c) const { co[t] = c; }
+
+  // the warp's `nvalid` rows of one array (row length rl) are one contiguous block in global memory
+  __device__ __forceinline__ void store_block(real *g, const real *lane_row, int rl) const {
+    if (g == nullptr) return;
+    const real *tile = lane_row - lane * rl;
+    const unsigned bytes = (unsigned)(nvalid * rl * (int)sizeof(real));
+    if ((bytes & 15u) == 0) {
+      if (lane == 0) bulk_store(g, tile, bytes);
+    } else {  // ragged last warp: coalesced element copies
+      for (int i = lane; i < nvalid * rl; i += 32) g[i] = tile[i];
+    }
+  }
+  __device__ __forceinline__ void drain() const {   // the tiles must outlive the copies that read them
+    if (lane == 0) {
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+    __syncwarp();
+  }
+  // called by all 32 lanes between the backward sweep and the rollout: write out policy and value function, free region B
+  __device__ __forceinline__ void between() const {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy tile writes -> visible to the bulk-copy engine
+    __syncwarp();
+    store_block(gK, Kt, T * M * N); store_block(gk, kt, T * M);
+    store_block(gV, Vt, T * N * N); store_block(gv, vt, T * N); store_block(gc, ct, T);
+    drain();
+  }
+  __device__ __forceinline__ void finish() const {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    store_block(gs, st, (T + 1) * N); store_block(ga, ac, T * M); store_block(gco, co, T + 1);
+    drain();
+  }
 };
 
 // LQR.backward (lqr.py:59-129) + LQR.forward (:131-161) of problem b, all matrices in registers
@@ -281,6 +333,7 @@ __device__ __forceinline__ int lqr_small_solve(int64_t b, int T, const real *__r
     out.put_gain(t, K, k);
     out.put_value(t, V, v, cst);
   }
+  out.between();
   // forward, :131-161
   real x[N], z[NM];
 #pragma unroll
@@ -347,13 +400,7 @@ __global__ void __launch_bounds__(kThreads) k_lqr_small(int64_t B, int T, const 
   if (status) status[b] = st;
 }
 
-// shared -> global bulk store of `bytes` (multiple of 16, both addresses 16-byte aligned), issued by one lane
-__device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, unsigned bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"((unsigned)__cvta_generic_to_shared(ssrc)), "r"(bytes)
-               : "memory");
-}
-
-constexpr int kStagedThreads = 64;  // 2 warps x 24 KB of tiles (C2: T = 10) -> 4 CTAs per SM
+constexpr int kStagedThreads = 64;  // 2 warps x 16.6 KB of tiles (C2: T = 10) -> 6 CTAs = 12 warps per SM
 
 template <int N, int M>
 __global__ void __launch_bounds__(kStagedThreads) k_lqr_small_staged(int64_t B, int T, const real *__restrict__ Fp, int64_t sF,
@@ -365,41 +412,15 @@ __global__ void __launch_bounds__(kStagedThreads) k_lqr_small_staged(int64_t B, 
                                                                       real *__restrict__ csto, int32_t *__restrict__ status) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
-  const bool value = Vo != nullptr;
-  const int64_t row = TileOut<N, M>::row_reals(T, true);   // tiles are carved for the full set; unused ones stay untouched
-  real *base = reinterpret_cast<real *>(smem_raw) + (int64_t)wq * 32 * row;
+  real *base = reinterpret_cast<real *>(smem_raw) + (int64_t)wq * 32 * TileOut<N, M>::row_reals(T);
   const int64_t b0 = ((int64_t)blockIdx.x * (kStagedThreads / 32) + wq) * 32;
   if (b0 >= B) return;
-  const int64_t b = b0 + lane;
   const int nvalid = (int)min((int64_t)32, B - b0);
-  const TileOut<N, M> out(base, lane, T, value);
-  int st = 0;
-  if (lane < nvalid) st = lqr_small_solve<N, M>(b, T, Fp, sF, fp, sf, Cp, sC, cp, sc, x0, terminal_zero, out);
+  const int64_t b = b0 + min(lane, nvalid - 1);   // padding lanes of the last warp shadow its last problem (their rows are never stored)
+  const TileOut<N, M> out(base, lane, nvalid, T, b0, states, actions, costs, Ko, ko, Vo, vo, csto);
+  const int st = lqr_small_solve<N, M>(b, T, Fp, sF, fp, sf, Cp, sC, cp, sc, x0, terminal_zero, out);
   if (status && lane < nvalid) status[b] = st;
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy tile writes -> visible to the bulk-copy engine
-  __syncwarp();
-  // the warp's 32 rows of every output array are one contiguous block in global memory
-  real *tiles[8] = {base, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  const int rl[8] = {(T + 1) * N, T * M, T + 1, T * M * N, T * M, T * N * N, T * N, T};
-  real *gl[8] = {states, actions, costs, Ko, ko, Vo, vo, csto};
-#pragma unroll
-  for (int a = 1; a < 8; a++) tiles[a] = tiles[a - 1] + 32 * rl[a - 1];
-#pragma unroll
-  for (int a = 0; a < 8; a++) {
-    if (gl[a] == nullptr) continue;
-    real *g = gl[a] + b0 * rl[a];
-    const unsigned bytes = (unsigned)(nvalid * rl[a] * (int)sizeof(real));
-    if ((bytes & 15u) == 0) {
-      if (lane == 0) bulk_store(g, tiles[a], bytes);
-    } else {  // ragged last warp: coalesced element copies
-      for (int i = lane; i < nvalid * rl[a]; i += 32) g[i] = tiles[a][i];
-    }
-  }
-  if (lane == 0) {
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the tiles must outlive the copies that read them
-  }
-  __syncwarp();
+  out.finish();
 }
 
 // ---------------------------------------------------------------- generic warp-per-problem kernel
@@ -669,7 +690,8 @@ int lqr_solve_launch(int64_t B, int n, int m, int T, const real *F, int64_t sF, 
   if (V && !(v && cst)) return tfmpc_set_error(TFMPC_E_INVALID, "V, v and cst must be given together");
   const bool small = (n == 2 && m == 2) || (n == 3 && m == 2);
   // staged variant: tiles of 32 rows per warp must fit shared memory and every output block must be 16-byte aligned
-  const int64_t row_reals = (int64_t)(T + 1) * n + (int64_t)T * m + (T + 1) + (int64_t)T * (m * n + m) + (int64_t)T * (n * n + n + 1);
+  const int64_t regA = (int64_t)T * (m * n + m), regB1 = (int64_t)T * (n * n + n + 1), regB2 = (int64_t)(T + 1) * n + (int64_t)T * m + (T + 1);
+  const int64_t row_reals = regA + std::max(regB1, regB2);   // TileOut::row_reals
   const size_t staged_smem = (size_t)(kStagedThreads / 32) * 32 * row_reals * sizeof(real);
   auto aligned16 = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
   const bool staged = small && staged_smem <= 100 * 1024 && aligned16(states) && aligned16(actions) && aligned16(costs) && aligned16(K) &&

@@ -371,7 +371,6 @@ def run_ours(args):
     streams = [torch.cuda.Stream(device=dev) for _ in range(S)]
     main = torch.cuda.current_stream()
     use_async = args.pipeline == "async" and args.workload in ("c3",) and S > 1
-    outs_k = None   # (per-step output sets were measured at 2 GPUs: slower than the ring, 280 M/s against 413 M/s)
     if use_async:
         works = [ops.ilqr_workspace(nat, B, T, dev) for _ in range(S)]
         done = [torch.cuda.Event() for _ in range(S)]
@@ -383,13 +382,12 @@ def run_ours(args):
     totals_all = torch.empty(S, B, device=dev) if world > 1 else None
     iters_all = torch.empty(S, B, dtype=torch.int32, device=dev) if world > 1 else None
     gathered = ([torch.empty_like(totals_all) for _ in range(world)], [torch.empty_like(iters_all) for _ in range(world)]) if world > 1 else None
-    step_no, step_lock = [0], threading.Lock()
 
     extra = os.environ.get("TFMPC_BENCH_EXTRA", "")   # diagnostics: what an op between two solves of a stream costs
     xbuf = torch.empty(B, device=dev)
 
-    def step(slot, k=None):
-        ops.ilqr_solve(nat, x0, u0, opts, outs[slot] if (k is None or outs_k is None) else outs_k[k])
+    def step(slot, k=None):   # k: index of the timed step (unused by the solve itself)
+        ops.ilqr_solve(nat, x0, u0, opts, outs[slot])
         if extra == "ops":
             torch.sum(outs[slot]["costs"], dim=1, out=xbuf)
         elif extra == "event":
@@ -464,20 +462,14 @@ def run_ours(args):
         st.wait_event(e0)
     tl = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     t_issue0 = time.perf_counter()
-    call_ms = []
     if use_async:
         # ONE stream, K back-to-back tfmpc_ilqr_solve_async calls over a ring of S output/workspace slots: the heads run one
         # after another on `main`, each batch's stragglers on the library's priority streams; `done[slot]` guards slot reuse.
-        # N > 1: every step keeps its own output set (K x 94 MB), so that nothing but the solves is enqueued while they run
-        # (side-stream reductions per step were measured: they alias hardware channels with the straggler streams and stall
-        # the head stream, -8 %); the [K, B] totals are formed after the last batch, then gathered.
         for k in range(args.steps):
             slot = k % S
             if k >= S:
-                main.wait_event(done[slot])       # the workspace of this slot is free again
-            t_call = time.perf_counter()
-            ops.ilqr_solve_async(nat, x0, u0, outs_k[k] if outs_k else outs[slot], works[slot], done[slot], opts)
-            call_ms.append(round(1e3 * (time.perf_counter() - t_call), 3))
+                main.wait_event(done[slot])       # outputs and workspace of this slot are free again
+            ops.ilqr_solve_async(nat, x0, u0, outs[slot], works[slot], done[slot], opts)
         for k in range(max(0, args.steps - S), args.steps):
             main.wait_event(done[k % S])
     elif args.issue == "threads" and S > 1:      # one issuing host thread per stream (ctypes drops the GIL inside the C call)
@@ -633,7 +625,7 @@ def run_ours(args):
                                "latency_ms_per_batch": seq_ms / args.steps, "step_ms": step_ms},
                 "per_rank": ({"columns": ["pipelined ms/step", "sequential ms/batch", "problem-iterations per batch", "final all-gather ms (incl. waiting for the slowest rank)", "host enqueue ms/step"], "ranks": per_rank}
                              if per_rank else None),
-                "host_enqueue_ms_per_step": issue_ms / args.steps, "host_ms_per_async_call": call_ms,
+                "host_enqueue_ms_per_step": issue_ms / args.steps,
                 "pipeline_timeline_ms": {"columns": ["stream", "start", "end"], "steps": timeline},
                 "roofline": roofline,
                 "e2e": {"value": e2e_value, "unit": "problem-iterations/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -265,6 +265,11 @@ def run_c2(args):
         peaks, peak_src = measured_peaks()
         byts = B * (24 + 4 * ((T + 1) * 2 + T * 2 + (T + 1) + 1 + T * (4 + 2 + 4 + 2 + 1)))
         ach = byts / (total_ms / args.steps * 1e-3) / 1e9
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, "profiles", "r01_traffic_c2.json")
+        if os.path.exists(tpath):      # DRAM bytes per problem measured once with ncu (provenance inside the file)
+            tr = json.load(open(tpath))
+            traffic, traffic_src = tr["dram_bytes_per_problem"] * B, tr["source"]
         line = {"metric": "batched LQR problems/sec", "value": value, "unit": "problems/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
@@ -274,7 +279,8 @@ def run_c2(args):
                            "status_nonzero": int((out["status"] != 0).sum())},
                 "step_ms": step_ms,
                 "roofline": {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
-                             "traffic": None, "peak_source": peak_src, "kernel": "k_lqr_small<2,2> (thread per problem, backward + forward fused)",
+                             "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                             "kernel": "k_lqr_small_staged<2,2> (thread per problem, backward + forward fused, TMA bulk stores)",
                              "algorithmic_bytes_per_problem": byts // B},
                 "e2e": {"value": B * world * args.steps / float(te[0]), "unit": "problems/s", "h2d_bytes_per_step": int(x0_pin.numel() * 4 + c.numel() * 4),
                         "d2h_bytes_per_step": int(sum(v.numel() * 4 for v in ho.values())), "api": "tfmpc_lqr_solve_host (pinned host buffers in and out, synchronous), one call per step"},

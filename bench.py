@@ -137,7 +137,7 @@ def cpu_baseline(name, T, sample, threads=0, repeats=1):
     cfg = workload_cfg(name)
     x0, u0 = make_inputs(cfg, sample, T, seed=12345)
     env = o.make_env(cfg)
-    cores = o.max_threads() if threads <= 0 else threads
+    cores = max(o.max_threads(), len(os.sched_getaffinity(0))) if threads <= 0 else threads   # every host core the process may use
     best = None
     for _ in range(repeats):
         t0 = time.perf_counter()
@@ -187,7 +187,7 @@ def c2_cpu(B, T, threads=0):
     goal, x0 = c2_inputs(B, 12345)
     F = np.concatenate([np.eye(2), np.eye(2)], axis=1)
     c = np.concatenate([-2 * goal, np.zeros_like(goal)], axis=1)
-    cores = o.max_threads() if threads <= 0 else threads
+    cores = max(o.max_threads(), len(os.sched_getaffinity(0))) if threads <= 0 else threads   # every host core the process may use
     t0 = time.perf_counter()
     o.lqr_solve(F, np.zeros(2), np.diag([2.0, 2.0, 10.0, 10.0]), c, x0, T, nthreads=cores)
     dt = time.perf_counter() - t0
@@ -540,7 +540,7 @@ def run_ours(args):
 
     # ---- end to end through the public host-buffer API: pinned host inputs -> results in host memory, every step.
     #      S host threads, each with its own env handle and stream (the C ABI is re-entrant across streams).
-    e2e_steps = max(S, min(args.steps, 4 * S))
+    e2e_steps = max(S, min(args.steps, 8 * S))
     nats = [envs.make_env(cfg).native() for _ in range(S)]
     houts = [new_out(host=True) for _ in range(S)]
 
@@ -654,7 +654,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=0, help="timed steps (default: 32 for the GPU arm -- the pipeline needs a few waves of 8 "
+    ap.add_argument("--steps", type=int, default=0, help="timed steps (default: 64 for the GPU arm -- the pipeline needs a few waves of 8 "
                     "batches to reach its steady state --, 5 for the CPU reference arm)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
@@ -670,7 +670,7 @@ def main():
     ap.add_argument("--streams", type=int, default=8, help="CUDA streams the independent steps are pipelined over (1 = strictly sequential)")
     args = ap.parse_args()
     if args.steps <= 0:
-        args.steps = 5 if (args.impl == "reference" or args.workload == "c5") else 32
+        args.steps = 5 if (args.impl == "reference" or args.workload == "c5") else 64
     if args.impl == "reference":
         run_reference(args)
     elif args.workload == "c2":

@@ -190,3 +190,23 @@ def test_trajectory_container(tmp_path):
     assert np.allclose(df["x[2]"].values, s[1:, 1, 0]) and np.allclose(df["costs"].values, c[:-1])
     bt = BatchTrajectory(np.stack([s[..., 0]] * 4), np.stack([a[..., 0]] * 4), np.stack([c] * 4), iterations=np.arange(4))
     assert len(bt) == 4 and np.allclose(bt.total_cost, c.sum()) and np.allclose(bt[1].states, tr.states)
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours) prints one JSON line with the contract keys,
+    on a small sample so that the CPU suite stays fast."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload", "c4", "--steps", "1", "--warmup", "0",
+                          "--cpu-sample", "32"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "dtype", "data",
+                "config", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0

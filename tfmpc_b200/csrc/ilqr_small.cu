@@ -3,9 +3,8 @@
 // Why thread-per-problem: the headline workload (BASELINE config C3) has n = m = 2, so one
 // problem's Riccati state (V_xx: 3 unique values, V_x: 2, K: 4, k: 2) fits in a handful of
 // registers and a warp-per-problem mapping would idle 30 of 32 lanes (SURVEY.md section 7,
-// "hard parts").  Data layout: the per-problem trajectories live in a struct-of-arrays
-// workspace ws[row][slot] with the problem slot fastest, so the 32 lanes of a warp read and
-// write 32 consecutive words (one 128-byte line) for every row they touch.
+// "hard parts").  Data layout: the solve workspace is made of 16-byte vector chunks (R4, small_core.cuh) --
+// trajectories [set][t][slot][lane], gains [t][slot][chunk] -- see struct WS below and DESIGN.md section 4.
 #include <algorithm>
 #include <atomic>
 #include <mutex>
@@ -75,9 +74,9 @@ __global__ void __launch_bounds__(kThreads) k_forward(EnvSmall e, int64_t B, int
 //                      alphas run only for the groups that rejected all of them.  The group leader then
 //                      applies the mu/delta schedule and convergence tests (tick_finish) and re-appends the
 //                      problem to the next tick's active list (warp-aggregated atomic).
-// Accepting a candidate is a buffer-index switch (p.cur), not a copy: each problem owns 1 + GA
-// trajectory buffers.  Converged problems drop out of the list, so late ticks touch few problems and
-// cost only their launch latency.
+// Accepting a candidate is a buffer-index switch (p.cur), not a copy: each problem owns two sets of GA
+// trajectory buffers; the nominal is the accepted member of the set that is not being written.  Converged
+// problems drop out of the list, so late ticks touch few problems and cost only their latency.
 constexpr int GA = 4;            // line-search lanes (and candidate buffers) per problem
 constexpr int NBUF = 2 * GA;      // two candidate sets of GA trajectories; the nominal is one member of the set not being written
 constexpr int kExtraTicks = 24;  // ticks beyond max_iterations available to regularisation retries (ilqr.py:267-270)

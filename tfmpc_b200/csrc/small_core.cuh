@@ -832,6 +832,7 @@ HD void forward_step(const EnvSmall &e, real alpha, const NomRec<N, M> &r, int t
   for (int i = 0; i < N; i++) x[i] = xn[i];
 }
 
+// (Stage API and host emulation; the solve's line search uses rollout_staged() in ilqr_small.cu instead.)
 // The records are loaded TWO steps ahead of their use through a 3-slot register ring; the loop is unrolled by 3 so
 // that the ring needs no register-to-register rotation (a rotating MOV would wait on the load it copies from and
 // collapse the prefetch distance to one step -- seen as 73% of the stall samples of the line-search kernel in ncu).

@@ -64,3 +64,25 @@ def test_device_logic_matches_oracle_on_a_batch(emul, prec):
     relc = np.abs(c.sum(1) - r["costs"].sum(1)) / np.abs(r["costs"].sum(1))
     assert np.all(relc[same] < 1e-5)
     assert (st[same, 1] == r["n_backward"][same]).all() and (st[same, 2] == r["n_rollouts"][same]).all()
+
+
+@pytest.mark.parametrize("prec", ["f32", "f64"])
+@pytest.mark.parametrize("T", [1, 2, 3, 4, 7])
+def test_device_logic_short_horizons(emul, prec, T):
+    """Horizons shorter than the prefetch depth of the rollouts (3-slot ring, loads two steps ahead) and of the backward
+    sweep (one step ahead): the shared device code must not read past the trajectory and must agree with the oracle."""
+    from oracle import oracle
+    from tfmpc_b200.envs import synthetic
+    o = oracle.Oracle(prec)
+    cfg = synthetic.navigation_config()
+    rng = np.random.RandomState(100 + T)
+    B = 64
+    x0 = synthetic.sample_x0(cfg, B, rng)
+    u0 = synthetic.sample_u_init([-1, -1], [1, 1], B, T, rng) * np.ones((1, 1, 2))
+    r = o.ilqr_solve(o.make_env(cfg), x0, u0)
+    s, a, c, st = emul(prec, cfg, x0, u0)
+    same = st[:, 0] == r["iterations"]
+    assert same.mean() >= (0.97 if prec == "f32" else 1.0)
+    relc = np.abs(c.sum(1) - r["costs"].sum(1)) / np.maximum(np.abs(r["costs"].sum(1)), 1e-6)
+    assert np.all(relc[same] < 1e-5)
+    assert (st[same, 1] == r["n_backward"][same]).all() and (st[same, 2] == r["n_rollouts"][same]).all()

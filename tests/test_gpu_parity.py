@@ -485,6 +485,48 @@ def test_ilqr_graph_replay_matches_direct_launches(prec, request):
             assert torch.equal(first[k], ref_b[k]), k
 
 
+# ------------------------------------------------------------------ edge cases: shortest horizons, ragged and empty batches
+@pytest.mark.parametrize("T", [1, 2, 3, 9])
+def test_ilqr_short_horizons_ragged_batch(prec, orc, T):
+    """Horizons shorter than the line search's shared-memory ring (8 steps) and the register prefetch, with a batch that
+    fills neither a warp nor a line-search group evenly."""
+    from tfmpc_b200.envs import synthetic
+    g, r = _solve_both(synthetic.navigation_config(), prec, orc, 37, T, seed=40 + T)
+    a = _agreement(g["stats"][:, 0], g["costs"].sum(1), r["iterations"], np.maximum(r["costs"].sum(1), 1e-6))
+    same = a["d"] == 0
+    assert a["same"] >= tol(prec, 0.9, 1.0), a["same"]
+    assert np.all(a["relc"][same] < tol(prec, 1e-4, 1e-6))
+    assert np.max(np.abs(g["actions"] - r["actions"])[same]) < tol(prec, 1e-3, 1e-5)
+
+
+@pytest.mark.parametrize("B", [1, 33, 45, 64])
+def test_lqr_ragged_batches_and_shortest_horizon(prec, orc, B):
+    """The TMA-staged LQR kernel with a ragged last warp (bulk stores need 16-byte multiples; other sizes fall back to
+    element copies), at T = 1 and T = 10."""
+    from tfmpc_b200 import envs
+    rng = np.random.RandomState(B)
+    goal, x0 = rng.uniform(-10, 10, size=(B, 2)), rng.normal(size=(B, 2))
+    F = np.concatenate([np.eye(2), np.eye(2)], axis=1)
+    c = np.concatenate([-2 * goal, np.zeros_like(goal)], axis=1)
+    for T in (1, 10):
+        out = envs.make_lqr_linear_navigation(goal, 5.0, dtype=_dt(prec)).solve_device(x0, T, want_policy=True, want_value=True)
+        r = orc.lqr_solve(F, np.zeros(2), np.diag([2.0, 2.0, 10.0, 10.0]), c, x0, T)
+        for key in ("states", "actions", "costs", "K", "k", "V", "v", "const"):
+            assert rel(_np(out[key]), r[key]) < tol(prec, 1e-5, 1e-12), (key, T)
+
+
+def test_empty_batch(prec):
+    from tfmpc_b200 import envs, ops
+    from tfmpc_b200.envs import synthetic
+    nat = _env(synthetic.navigation_config(), prec).native(_dt(prec))
+    out = ops.ilqr_solve(nat, torch.empty(0, 2, dtype=_dt(prec), device="cuda"), torch.empty(0, 5, 2, dtype=_dt(prec), device="cuda"))
+    assert out["states"].shape == (0, 6, 2) and out["stats"].shape == (0, 4)
+    lq = envs.make_lqr_linear_navigation(np.zeros((1, 2)), 5.0, dtype=_dt(prec))
+    F, f, Cm, c = lq._device_params()
+    out = ops.lqr_solve(F, f, Cm, c.reshape(-1)[:4], torch.empty(0, 2, dtype=_dt(prec), device="cuda"), 3)
+    assert out["actions"].shape == (0, 3, 2)
+
+
 # ------------------------------------------------------------------ full-size properties
 def test_full_size_nav_properties():
     """BASELINE config C3 at full size (B = 65,536, H = 50), fp32: size-independent properties."""

@@ -58,6 +58,8 @@ def lqr_solve(F, f, Cm, c, x0, T, terminal_zero=False, want_policy=True, want_va
             out["V"] = _empty(x0, B, T, n, n)
             out["v"] = _empty(x0, B, T, n)
             out["const"] = _empty(x0, B, T)
+    if B == 0:       # nothing to solve: empty results, no launch (an empty tensor has no device pointer to hand over)
+        return out
     P = lambda t, i32=False: N.dev_ptr(lib, t, i32)  # noqa: E731
     ptrs = [P(F), P(f), P(Cm), P(c), P(x0), P(out["states"]), P(out["actions"]), P(out["costs"]), P(out.get("K")), P(out.get("k")),
             P(out.get("V")), P(out.get("v")), P(out.get("const")), P(out["status"], True)]
@@ -234,6 +236,8 @@ def ilqr_solve(env, x0, u_init, opts=None, out=None):
     if out is None:
         out = dict(states=_empty(x0, B, T + 1, env.n), actions=_empty(x0, B, T, env.m), costs=_empty(x0, B, T + 1),
                    stats=torch.empty(B, 4, dtype=torch.int32, device=x0.device))
+    if B == 0:
+        return out
     nbytes = lib.tfmpc_ilqr_workspace_bytes(env.handle, C.c_int64(B), T)
     if nbytes < 0:
         N.check(lib, int(nbytes))

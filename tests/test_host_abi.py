@@ -80,6 +80,14 @@ def test_argument_validation_and_error_strings(built):
     assert lib.tfmpc_env_create(2, 40, 40, 0, arr, C.c_int64(3), C.byref(h)) == -1
     assert lib.tfmpc_lqr_solve(C.c_int64(1), 2, 2, 10, None, C.c_int64(0), None, C.c_int64(0), None, C.c_int64(0), None, C.c_int64(0),
                                None, 0, None, None, None, None, None, None, None, None, None, None) == -1
+    # asynchronous solve: a completion event is mandatory, and all the synchronous form's argument checks apply
+    dummy = C.c_void_p(0x1000)
+    assert lib.tfmpc_ilqr_solve_async(None, C.c_int64(1), 5, dummy, dummy, None, dummy, dummy, dummy, dummy, dummy, C.c_int64(1 << 20), None, None) == -1
+    assert b"completion event" in lib.tfmpc_last_error()
+    assert lib.tfmpc_ilqr_solve_async(None, C.c_int64(1), 5, dummy, dummy, None, dummy, dummy, dummy, dummy, dummy, C.c_int64(1 << 20), None, dummy) == -1
+    assert b"bad argument" in lib.tfmpc_last_error()
+    # graph mode is a plain switch that reports the previous state (off by default)
+    assert lib.tfmpc_set_graph_mode(1) == 0 and lib.tfmpc_set_graph_mode(0) == 1 and lib.tfmpc_set_graph_mode(0) == 0
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")

@@ -71,7 +71,8 @@ enum {
   TFMPC_ST_MAXITER = 1,     /* max_iterations exhausted (ilqr.py:227) */
   TFMPC_ST_NONPD = 2,       /* a box-QP / inverse factorisation failed (optimization.py:47-51; the reference aborts) */
   TFMPC_ST_REGLOOP = 3,     /* regularisation loop guard tripped (the reference would spin, ilqr.py:238) */
-  TFMPC_ST_NAN = 4          /* NaN in the gradient norm */
+  TFMPC_ST_NAN = 4,         /* NaN in the gradient norm */
+  TFMPC_ST_ABORTED = 5      /* the solve kernel gave up before this problem finished (device watchdog); results undefined */
 };
 
 typedef struct tfmpc_env tfmpc_env_t; /* opaque */
@@ -207,6 +208,21 @@ int64_t tfmpc_ilqr_workspace_bytes(const tfmpc_env_t *env, int64_t B, int T);
 int tfmpc_ilqr_solve(const tfmpc_env_t *env, int64_t B, int T, const tfmpc_real *x0, const tfmpc_real *u_init,
                      const tfmpc_ilqr_opts_t *opts, tfmpc_real *states, tfmpc_real *actions, tfmpc_real *costs,
                      int32_t *stats, void *workspace, int64_t workspace_bytes, void *stream);
+/* Runtime options of the small-environment solve (NavigationLQR n <= 4, Navigation).  Returns the previous value, or
+ * TFMPC_E_INVALID for an unknown name.  Options and their environment-variable defaults:
+ *   "solver"             1 = persistent work-queue kernel (default), 0 = per-tick launch sequence (round-1 path)   TFMPC_SOLVER=queue|ticks
+ *   "qp"                 box-QP of the constrained controller (ilqr.py:364-387) for m <= 2:
+ *                        2 = closed form (default of the fp32 build), 0 = the reference's projected-Newton iteration
+ *                        (optimization.py:6-101; default of the fp64 verification build)                        TFMPC_QP=closed|newton
+ *   "queue_warps_per_sm" resident warps per SM of the queue kernel (default 16)                                  TFMPC_QUEUE_WPS
+ *   "queue_w_target"     warps the queue plans its pop size for (0 = 8 per SM)                                   TFMPC_QUEUE_WTARGET
+ *   "queue_patience"     idle polls before a warp takes fewer problems than planned                              TFMPC_QUEUE_PATIENCE */
+int tfmpc_set_option(const char *name, int value);
+/* Diagnostics: copies the control block the queue solver left in `workspace` (after the solve has completed on `stream`):
+ * out[0] = warp iterations, out[1] = problem iterations (lanes), out[2] = rollout rounds incl. store passes,
+ * out[3] = store passes (problems), out[4] = watchdog flag.  Synchronises the stream. */
+int tfmpc_ilqr_queue_counters(const void *workspace, int32_t *out, void *stream);
+
 /* CUDA-graph replay of the tick solve's launch sequence (small environments): with on != 0 the second and later calls
  * with the same (environment, B, T, options, buffer addresses) replay two captured graphs instead of enqueueing 253
  * kernels (host cost per solve 1.4 ms -> 0.3 ms, results bit-identical).  Off by default;

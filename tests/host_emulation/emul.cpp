@@ -27,7 +27,7 @@ static void fill_env(EnvSmall &s, int kind, int n, int nz, const double *p) {
   for (int i = 0; i < n; i++) if (std::isinf((double)s.low[i]) || std::isinf((double)s.high[i])) s.bounded = 0;
 }
 
-template <int KIND, int N, int M>
+template <int KIND, int N, int M, int QP>
 static void run(const EnvSmall &e, const IlqrOpts &o, int64_t B, int T, const real *x0, const real *u_init, real *states, real *actions,
                 real *costs, int32_t *stats) {
   // same vector-record workspace addressing as the CUDA solve kernels (chunk-major, slot fastest)
@@ -41,7 +41,7 @@ static void run(const EnvSmall &e, const IlqrOpts &o, int64_t B, int T, const re
     VecGain<N, M> gain = {ws.data() + 2 * nomch * S + b * chg, S * chg, 1};                           // [t][slot][chunk]
     const CostSink none = {nullptr, 0};
     start_pass<KIND, N, M>(e, T, x0 + b * N, u_init + b * nu, traj[0], none);
-    int cur = solve_one<KIND, N, M>(e, o, T, traj, gain, stats + b * 4);
+    int cur = solve_one<KIND, N, M, QP>(e, o, T, traj, gain, stats + b * 4);
     real x[N], u[M];
     for (int t = 0; t < T; t++) {
       traj[cur].load_xu(t, x, u);
@@ -55,18 +55,29 @@ static void run(const EnvSmall &e, const IlqrOpts &o, int64_t B, int T, const re
   }
 }
 
-extern "C" int emul_ilqr_solve(int kind, int n, int nz, const double *params, double atol, int max_iterations, double mu_min, double delta_0,
-                               double c1, const double *alphas, int64_t B, int T, const real *x0, const real *u_init, real *states,
-                               real *actions, real *costs, int32_t *stats) {
+// qp_mode: 0 = the reference's projected-Newton box-QP (QP_NEWTON), 2 = closed form for m <= 2 (QP_CLOSED)
+extern "C" int emul_ilqr_solve_qp(int kind, int n, int nz, const double *params, double atol, int max_iterations, double mu_min, double delta_0,
+                                  double c1, const double *alphas, int64_t B, int T, const real *x0, const real *u_init, real *states,
+                                  real *actions, real *costs, int32_t *stats, int qp_mode) {
   EnvSmall e;
   fill_env(e, kind, n, nz, params);
   IlqrOpts o;
   o.atol = (real)atol; o.c1 = (real)c1; o.max_iterations = max_iterations; o.mu_min = mu_min; o.delta_0 = delta_0;
   for (int i = 0; i < N_ALPHA; i++) o.alphas[i] = (real)alphas[i];
-  if (kind == TFMPC_ENV_NAVIGATION && n == 2) run<TFMPC_ENV_NAVIGATION, 2, 2>(e, o, B, T, x0, u_init, states, actions, costs, stats);
-  else if (kind == TFMPC_ENV_NAVLQR && n == 2) run<TFMPC_ENV_NAVLQR, 2, 2>(e, o, B, T, x0, u_init, states, actions, costs, stats);
-  else if (kind == TFMPC_ENV_NAVLQR && n == 3) run<TFMPC_ENV_NAVLQR, 3, 3>(e, o, B, T, x0, u_init, states, actions, costs, stats);
+  const bool closed = qp_mode == QP_CLOSED;
+  if (kind == TFMPC_ENV_NAVIGATION && n == 2) {
+    if (closed) run<TFMPC_ENV_NAVIGATION, 2, 2, QP_CLOSED>(e, o, B, T, x0, u_init, states, actions, costs, stats);
+    else run<TFMPC_ENV_NAVIGATION, 2, 2, QP_NEWTON>(e, o, B, T, x0, u_init, states, actions, costs, stats);
+  } else if (kind == TFMPC_ENV_NAVLQR && n == 2) {
+    if (closed) run<TFMPC_ENV_NAVLQR, 2, 2, QP_CLOSED>(e, o, B, T, x0, u_init, states, actions, costs, stats);
+    else run<TFMPC_ENV_NAVLQR, 2, 2, QP_NEWTON>(e, o, B, T, x0, u_init, states, actions, costs, stats);
+  } else if (kind == TFMPC_ENV_NAVLQR && n == 3) run<TFMPC_ENV_NAVLQR, 3, 3, QP_NEWTON>(e, o, B, T, x0, u_init, states, actions, costs, stats);
   else return -2;
   return 0;
+}
+extern "C" int emul_ilqr_solve(int kind, int n, int nz, const double *params, double atol, int max_iterations, double mu_min, double delta_0,
+                               double c1, const double *alphas, int64_t B, int T, const real *x0, const real *u_init, real *states,
+                               real *actions, real *costs, int32_t *stats) {
+  return emul_ilqr_solve_qp(kind, n, nz, params, atol, max_iterations, mu_min, delta_0, c1, alphas, B, T, x0, u_init, states, actions, costs, stats, 0);
 }
 extern "C" int emul_real_bytes(void) { return (int)sizeof(real); }

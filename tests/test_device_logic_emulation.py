@@ -86,3 +86,114 @@ def test_device_logic_short_horizons(emul, prec, T):
     relc = np.abs(c.sum(1) - r["costs"].sum(1)) / np.maximum(np.abs(r["costs"].sum(1)), 1e-6)
     assert np.all(relc[same] < 1e-5)
     assert (st[same, 1] == r["n_backward"][same]).all() and (st[same, 2] == r["n_rollouts"][same]).all()
+
+
+# ------------------------------------------------------------------ closed-form box-QP and the persistent queue solver
+@pytest.fixture(scope="module")
+def emul2():
+    """(sequential solve_one, warp-emulated queue solver) with a box-QP flavour argument"""
+    subprocess.check_call(["bash", os.path.join(HERE, "host_emulation", "build.sh")])
+    libs = {p: C.CDLL(os.path.join(HERE, "host_emulation", f"libemul_{p}.so")) for p in ("f32", "f64")}
+    p = lambda z: z.ctypes.data_as(C.c_void_p)  # noqa: E731
+
+    def prep(prec, cfg, x0, u_init):
+        from oracle import oracle
+        dt = np.float32 if prec == "f32" else np.float64
+        kind, n, m, nz, params = oracle.pack_env(cfg)
+        x0 = np.ascontiguousarray(x0, dtype=dt); u = np.ascontiguousarray(u_init, dtype=dt)
+        B, T = u.shape[0], u.shape[1]
+        bufs = [np.zeros((B, T + 1, n), dt), np.zeros((B, T, m), dt), np.zeros((B, T + 1), dt), np.zeros((B, 4), np.int32)]
+        return kind, n, nz, np.ascontiguousarray(params, dtype=np.float64), x0, u, B, T, bufs
+
+    def seq(prec, cfg, x0, u_init, qp):
+        kind, n, nz, params, x0, u, B, T, bufs = prep(prec, cfg, x0, u_init)
+        rc = libs[prec].emul_ilqr_solve_qp(kind, n, nz, p(params), C.c_double(5e-3), 100, C.c_double(1e-6), C.c_double(2.0), C.c_double(0.0),
+                                          p(ALPHAS), C.c_int64(B), T, p(x0), p(u), *[p(b) for b in bufs], qp)
+        assert rc == 0
+        return bufs
+
+    def queue(prec, cfg, x0, u_init, qp, nwarps, w_target, patience=4):
+        kind, n, nz, params, x0, u, B, T, bufs = prep(prec, cfg, x0, u_init)
+        ctrl = np.zeros(libs[prec].emul_queue_ctrl_ints(), np.int32)
+        rc = libs[prec].emul_queue_solve(kind, n, nz, p(params), C.c_double(5e-3), 100, C.c_double(1e-6), C.c_double(2.0), C.c_double(0.0),
+                                        p(ALPHAS), B, T, p(x0), p(u), *[p(b) for b in bufs], qp, nwarps, w_target, patience, p(ctrl))
+        assert rc == 0, f"queue solver flagged {rc}"
+        return bufs, ctrl
+    return seq, queue
+
+
+def _nav_batch(B, T, seed):
+    from tfmpc_b200.envs import synthetic
+    cfg = synthetic.navigation_config()
+    rng = np.random.RandomState(seed)
+    return cfg, synthetic.sample_x0(cfg, B, rng), synthetic.sample_u_init([-1, -1], [1, 1], B, T, rng) * np.ones((1, 1, 2))
+
+
+@pytest.mark.parametrize("prec", ["f32", "f64"])
+def test_closed_form_qp_agreement_with_oracle(emul2, prec):
+    """QP_CLOSED (the fp32 product default) against the oracle's projected-Newton box-QP on the C3 recipe.
+    fp64: same iteration count >= 99 %, cost within 1e-4 >= 99.9 %.  fp32: at least as close to the fp64 oracle as the
+    fp32 oracle is (the closed form is the exact minimiser, the iteration stops early), minus one point."""
+    from oracle import oracle
+    seq, _ = emul2
+    cfg, x0, u0 = _nav_batch(2048, 50, 12345)
+    o64 = oracle.Oracle("f64")
+    r64 = o64.ilqr_solve(o64.make_env(cfg), x0, u0)
+    s, a, c, st = seq(prec, cfg, x0, u0, 2)
+    same64 = np.mean(st[:, 0] == r64["iterations"])
+    relc = np.abs(c.sum(1) - r64["costs"].sum(1)) / np.abs(r64["costs"].sum(1))
+    if prec == "f64":
+        assert same64 >= 0.99 and np.mean(relc <= 1e-4) >= 0.999, (same64, np.mean(relc <= 1e-4))
+        return
+    o32 = oracle.Oracle("f32")
+    r32 = o32.ilqr_solve(o32.make_env(cfg), x0, u0)
+    band = np.mean(r32["iterations"] == r64["iterations"])
+    assert same64 >= band - 0.01, (same64, band)
+    assert np.mean(st[:, 0] == r32["iterations"]) >= 0.95
+    assert np.mean(relc <= 1e-4) >= 0.985
+
+
+@pytest.mark.parametrize("prec", ["f32", "f64"])
+@pytest.mark.parametrize("qp", [0, 2])
+@pytest.mark.parametrize("B,T,nwarps,w_target", [(70, 50, 3, 2), (40, 50, 2, 4), (33, 1, 2, 1), (37, 7, 2, 1), (20, 9, 1, 1)])
+def test_queue_solver_equals_sequential_solve(emul2, prec, qp, B, T, nwarps, w_target):
+    """The persistent work-queue kernel body (queue_core.cuh), executed warp by warp on the CPU, must reproduce the sequential
+    per-problem composition solve_one() BIT FOR BIT: same arithmetic, different schedule (ticket queue, line-search rounds with
+    lanes shared between problems, store pass, cooperative line staging, partially filled warps, horizons shorter than a line)."""
+    seq, queue = emul2
+    cfg, x0, u0 = _nav_batch(B, T, 3 + B)
+    ref = seq(prec, cfg, x0, u0, qp)
+    got, ctrl = queue(prec, cfg, x0, u0, qp, nwarps, w_target)
+    for name, a, b in zip(("states", "actions", "costs", "stats"), ref, got):
+        assert np.array_equal(a, b), name
+    assert ctrl[64] == B and ctrl[0] == ctrl[32]             # every problem finished, every ticket consumed
+    assert ctrl[192] == int(got[3][:, 1].sum())              # one backward pass per popped problem
+
+
+@pytest.mark.parametrize("prec", ["f32", "f64"])
+@pytest.mark.parametrize("n,low,high,beta", [(1, -0.3, 0.3, 0.5), (2, -1.0, 1.0, 5.0), (3, -0.4, 0.6, 0.5), (4, None, None, 2.0), (2, None, None, 0.5)])
+def test_queue_solver_navlqr_sizes(emul2, prec, n, low, high, beta):
+    """NavigationLQR n = 1..4 (two-chunk trajectory records for n >= 3, unbounded = Cholesky controller) through the queue."""
+    from tfmpc_b200.envs import synthetic
+    seq, queue = emul2
+    goal = [1.0, -2.0, 3.0, 0.5][:n]
+    cfg = synthetic.navlqr_config(goal, beta, low, high)
+    rng = np.random.RandomState(n)
+    B, T = 45, 11
+    x0 = synthetic.sample_x0(cfg, B, rng)
+    lo = np.full(n, -np.inf if low is None else low); hi = np.full(n, np.inf if high is None else high)
+    u0 = synthetic.sample_u_init(lo, hi, B, T, rng)
+    qp = 2 if n <= 2 else 0
+    ref = seq(prec, cfg, x0, u0, qp) if n in (2, 3) else None     # the sequential harness instantiates n = 2, 3 only
+    got, ctrl = queue(prec, cfg, x0, u0, qp, 2, 1)
+    assert ctrl[64] == B
+    if ref is not None:
+        for a, b in zip(ref, got):
+            assert np.array_equal(a, b)
+    from oracle import oracle
+    o = oracle.Oracle(prec)
+    r = o.ilqr_solve(o.make_env(cfg), x0, u0)
+    same = got[3][:, 0] == r["iterations"]
+    assert same.mean() >= (0.9 if prec == "f32" else (0.97 if qp == 2 else 1.0)), same.mean()
+    relc = np.abs(got[2].sum(1) - r["costs"].sum(1)) / np.maximum(np.abs(r["costs"].sum(1)), 1e-9)
+    assert np.all(relc[same] < (1e-4 if prec == "f32" else 1e-8))

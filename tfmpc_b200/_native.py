@@ -22,7 +22,7 @@ _LIBS = {}
 _LOCK = threading.Lock()
 
 ENV_KIND = {"NavigationLQR": 0, "Navigation": 1, "Reservoir": 2, "HVAC": 3}
-STATUS = {0: "converged", 1: "max_iterations", 2: "non_pd", 3: "regularisation_loop", 4: "nan"}
+STATUS = {0: "converged", 1: "max_iterations", 2: "non_pd", 3: "regularisation_loop", 4: "nan", 5: "aborted"}
 
 
 class TfmpcError(RuntimeError):
@@ -59,6 +59,7 @@ def load(precision="f32"):
         lib.tfmpc_kernel_launch_count.restype = C.c_int64
         lib.tfmpc_ilqr_workspace_bytes.restype = C.c_int64
         lib.tfmpc_ilqr_workspace_bytes.argtypes = [C.c_void_p, C.c_int64, C.c_int]
+        lib.tfmpc_set_option.argtypes = [C.c_char_p, C.c_int]
         if lib.tfmpc_abi_version() != 1:
             raise TfmpcError("libtfmpc_b200 ABI version mismatch")
         want = 4 if precision == "f32" else 8

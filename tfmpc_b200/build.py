@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "lib")
 OBJ = os.path.join(HERE, "build")
-SOURCES = ["api.cu", "ilqr_small.cu", "ilqr_warp.cu", "env_ops.cu", "lqr.cu", "peak.cu", "backward_dense.cu"]
+SOURCES = ["api.cu", "ilqr_small.cu", "ilqr_queue.cu", "ilqr_warp.cu", "env_ops.cu", "lqr.cu", "peak.cu", "backward_dense.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 # fp32 product build: fast intrinsics (MUFU-based division / exp / sqrt, FTZ).  Measured on B200 ("numerics"):
 # 1.5x faster end to end and statistically indistinguishable parity -- same-iteration-count agreement with the fp32 oracle

@@ -63,6 +63,24 @@ int make_opts(const tfmpc_ilqr_opts_t *in, IlqrOpts *o) {
 }
 
 bool use_small(const tfmpc_env *e) { return e->small != 0; }
+
+int env_choice(const char *name, const char *a, int va, const char *b, int vb, int dflt) {
+  const char *v = getenv(name);
+  if (!v || !*v) return dflt;
+  if (!strcmp(v, a)) return va;
+  if (!strcmp(v, b)) return vb;
+  return atoi(v);
+}
+// solver: 1 = persistent work-queue kernel, 0 = per-tick launch sequence
+std::atomic<int> g_solver{env_choice("TFMPC_SOLVER", "queue", 1, "ticks", 0, 1)};
+// qp: 2 = closed form (m <= 2), 0 = the reference's projected-Newton iteration.  The fp64 verification build defaults to
+// the reference's iteration so that it reproduces the fp64 oracle exactly.
+#ifdef TFMPC_F64
+std::atomic<int> g_qp{env_choice("TFMPC_QP", "closed", 2, "newton", 0, 0)};
+#else
+std::atomic<int> g_qp{env_choice("TFMPC_QP", "closed", 2, "newton", 0, 2)};
+#endif
+bool use_queue(const tfmpc_env *e) { return use_small(e) && g_solver.load() != 0; }
 }  // namespace
 
 extern "C" {
@@ -315,9 +333,30 @@ int tfmpc_ilqr_backward_staged(int64_t B, int T, int n, int m, const double *low
                                dV2, status, (cudaStream_t)stream);
 }
 
+int tfmpc_set_option(const char *name, int value) {
+  if (!name) return tfmpc_set_error(TFMPC_E_INVALID, "tfmpc_set_option: null name");
+  if (!strcmp(name, "solver")) return g_solver.exchange(value ? 1 : 0);
+  if (!strcmp(name, "qp")) {
+    if (value != 0 && value != 2) return tfmpc_set_error(TFMPC_E_INVALID, "tfmpc_set_option: qp must be 0 (newton) or 2 (closed form)");
+    return g_qp.exchange(value);
+  }
+  int prev = 0;
+  if (queue_ilqr_option(name, value, &prev)) return prev;
+  return tfmpc_set_error(TFMPC_E_INVALID, "tfmpc_set_option: unknown option '%s'", name);
+}
+
+int tfmpc_ilqr_queue_counters(const void *workspace, int32_t *out, void *stream) {
+  REQ(workspace && out, "tfmpc_ilqr_queue_counters: null argument");
+  int raw[320];
+  int rc = queue_ilqr_counters(workspace, raw, 320, (cudaStream_t)stream);
+  if (rc) return rc;
+  out[0] = raw[160]; out[1] = raw[192]; out[2] = raw[224]; out[3] = raw[256]; out[4] = raw[128];
+  return TFMPC_OK;
+}
+
 int64_t tfmpc_ilqr_workspace_bytes(const tfmpc_env_t *e, int64_t B, int T) {
   if (!e || B < 0 || T < 1) return tfmpc_set_error(TFMPC_E_INVALID, "tfmpc_ilqr_workspace_bytes: bad argument");
-  int64_t b = use_small(e) ? small_ilqr_workspace_bytes(e, B, T)
+  int64_t b = use_queue(e) ? queue_ilqr_workspace_bytes(e, std::max<int64_t>(B, 1), T) : use_small(e) ? small_ilqr_workspace_bytes(e, B, T)
                            : (e->kind == TFMPC_ENV_NAVLQR ? dense_navlqr_workspace_bytes(e, B, T) : warp_ilqr_workspace_bytes(e, B, T));
   return (b + 255) / 256 * 256;
 }
@@ -334,6 +373,11 @@ static int ilqr_solve_impl(const tfmpc_env_t *e, int64_t B, int T, const real *x
   IlqrOpts o;
   int rc = make_opts(opts, &o);
   if (rc) return rc;
+  if (use_queue(e)) {   // one persistent kernel, wholly in stream order
+    rc = queue_ilqr_solve(e, B, T, x0, u_init, o, states, actions, costs, stats, ws, ws_bytes, g_qp.load(), s);
+    if (!rc && done) CUDA_TRY(cudaEventRecord(done, s));
+    return rc;
+  }
   if (use_small(e)) return small_ilqr_solve(e, B, T, x0, u_init, o, states, actions, costs, stats, ws, ws_bytes, s, done);
   // the persistent kernels run wholly in stream order
   rc = e->kind == TFMPC_ENV_NAVLQR ? dense_navlqr_solve(e, B, T, x0, u_init, o, states, actions, costs, stats, ws, ws_bytes, s)

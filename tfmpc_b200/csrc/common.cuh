@@ -18,8 +18,8 @@ typedef tfmpc_real real;
 #define HD inline
 #endif
 
-// ---- scalar math in the build's precision (no fast-math: parity budget is 1e-4 after
-// ~50 steps x ~20 iterations; see DESIGN.md "numerics")
+// ---- scalar math in the build's precision.  The fp32 product library is compiled with --use_fast_math (build.py:
+// MUFU-based division / exp / sqrt, FTZ), the fp64 verification build is IEEE; DESIGN.md "numerics" has the parity data.
 HD real r_abs(real v) { return v < 0 ? -v : v; }
 HD real r_max(real a, real b) { return a > b ? a : b; }
 HD real r_min(real a, real b) { return a < b ? a : b; }
@@ -125,6 +125,12 @@ void small_ilqr_forget(const tfmpc_env *e);   // drop the cached CUDA graphs of 
 // done != nullptr: asynchronous form -- `s` does not wait for the straggler ticks, `done` is recorded behind the results
 int small_ilqr_solve(const tfmpc_env *e, int64_t B, int T, const real *x0, const real *u_init, const IlqrOpts &o, real *states,
                      real *actions, real *costs, int32_t *stats, void *ws, int64_t ws_bytes, cudaStream_t s, cudaEvent_t done = nullptr);
+// persistent work-queue solve (ilqr_queue.cu); qp = QP_NEWTON / QP_CLOSED (small_core.cuh)
+int64_t queue_ilqr_workspace_bytes(const tfmpc_env *e, int64_t B, int T);
+int queue_ilqr_solve(const tfmpc_env *e, int64_t B, int T, const real *x0, const real *u_init, const IlqrOpts &o, real *states,
+                     real *actions, real *costs, int32_t *stats, void *ws, int64_t ws_bytes, int qp, cudaStream_t s);
+int queue_ilqr_option(const char *name, int value, int *previous);
+int queue_ilqr_counters(const void *ws, int *out, int n, cudaStream_t s);
 int small_boxqp(int64_t B, int m, const real *H, const real *q, const real *lo, const real *hi, real *x, real *Hfree, int32_t *isfree,
                 int32_t *nfree, int32_t *status, cudaStream_t s);
 

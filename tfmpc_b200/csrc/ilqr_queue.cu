@@ -1,0 +1,152 @@
+// Persistent work-queue iLQR solve for small environments: kernels and launcher around queue_core.cuh.
+// One solve = k_queue_init (control block, ring, default stats) + k_queue_solve (one warp per CTA, persistent).
+#include <algorithm>
+#include <atomic>
+#include <cstdlib>
+#include <cstring>
+
+#include "queue_core.cuh"
+
+namespace {
+
+#ifdef TFMPC_F64
+constexpr int kMaxWarpsPerSM = 8;    // WarpSmem is 19 KB in the fp64 build
+#else
+constexpr int kMaxWarpsPerSM = 16;   // 128 registers per thread
+#endif
+
+template <int KIND, int N, int M, int QP>
+__global__ void __launch_bounds__(32, kMaxWarpsPerSM) k_queue_solve(EnvSmall e, IlqrOpts o, tq::QParams q) {
+  __shared__ tq::WarpSmem sm;
+  WarpRT rt;
+  tq::queue_warp_main<KIND, N, M, QP>(rt, e, o, q, sm, (int)blockIdx.x);
+}
+
+__global__ void __launch_bounds__(256) k_queue_init(tq::QParams q, int nwarps) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < tq::C_INTS) q.ctrl[i] = i == tq::C_TAIL ? q.B : (i == tq::C_ALIVE ? nwarps : 0);
+  if (i <= q.ring_mask) q.ring[i] = 0ull;   // ticket field 0 never matches a re-queue ticket (those are >= B >= 1)
+  if (i < q.B) reinterpret_cast<int4 *>(q.stats)[i] = make_int4(0, 0, 0, TFMPC_ST_ABORTED);   // overwritten when the problem finishes
+}
+
+int env_int(const char *name, int dflt) {
+  const char *v = getenv(name);
+  return v && *v ? atoi(v) : dflt;
+}
+
+std::atomic<int> g_wps{env_int("TFMPC_QUEUE_WPS", kMaxWarpsPerSM)};
+std::atomic<int> g_w_target{env_int("TFMPC_QUEUE_WTARGET", 0)};   // 0 = 8 warps per SM
+std::atomic<int> g_patience{env_int("TFMPC_QUEUE_PATIENCE", 4)};
+
+int device_sms(int device) {
+  static int cached[64] = {0};
+  if (device >= 0 && device < 64 && cached[device]) return cached[device];
+  int v = 148;
+  cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device);
+  if (device >= 0 && device < 64) cached[device] = v;
+  return v;
+}
+
+struct Plan {
+  int nwarps, NL, row_r4, ch2;
+  unsigned cap;
+  int64_t o_ctrl, o_ring, o_prob, o_traj, o_gain, bytes;
+};
+
+Plan make_plan(const tfmpc_env *e, int64_t B, int T) {
+  Plan p;
+  const int n = e->n, m = e->m;
+  const int chn = (n + m + 3) / 4;
+  p.NL = ((T + 1) * chn + 7) / 8;
+  p.row_r4 = p.NL * 8;
+  p.ch2 = (m * n + m + 1) / 2;
+  const int wps = std::max(1, std::min(g_wps.load(), kMaxWarpsPerSM));
+  p.nwarps = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)device_sms(e->device) * wps, B));
+  p.cap = 1024;
+  while (p.cap < 2u * (unsigned)B) p.cap <<= 1;
+  auto al = [](int64_t v) { return (v + 255) / 256 * 256; };
+  int64_t off = 0;
+  p.o_ctrl = off; off += al((int64_t)tq::C_INTS * 4);
+  p.o_ring = off; off += al((int64_t)p.cap * 8);
+  p.o_prob = off; off += al(B * (int64_t)sizeof(tq::QProb));
+  p.o_traj = off; off += al(2 * B * p.row_r4 * (int64_t)sizeof(R4));
+  p.o_gain = off; off += al((int64_t)p.nwarps * T * p.ch2 * 32 * (int64_t)sizeof(tq::R2));
+  p.bytes = off;
+  return p;
+}
+
+template <int KIND, int N, int M>
+int launch(const tfmpc_env *e, int64_t B, int T, const real *x0, const real *u_init, const IlqrOpts &o, real *states, real *actions,
+           real *costs, int32_t *stats, void *ws, int qp, cudaStream_t s) {
+  const Plan pl = make_plan(e, B, T);
+  char *base = (char *)ws;
+  tq::QParams q;
+  q.ctrl = (int *)(base + pl.o_ctrl);
+  q.ring = (unsigned long long *)(base + pl.o_ring);
+  q.ring_mask = pl.cap - 1;
+  q.prob = (tq::QProb *)(base + pl.o_prob);
+  q.traj = (R4 *)(base + pl.o_traj);
+  q.gain = (tq::R2 *)(base + pl.o_gain);
+  q.B = (int)B; q.T = T; q.row_r4 = pl.row_r4;
+  const int wt = g_w_target.load();
+  q.w_target = wt > 0 ? wt : device_sms(e->device) * 8;
+  q.patience = std::max(0, g_patience.load());
+  q.watchdog_ns = 4000000000ull;   // 4 s without progress for one warp: give up (status TFMPC_ST_ABORTED) instead of hanging the device
+  q.x0 = x0; q.u_init = u_init; q.states = states; q.actions = actions; q.costs = costs; q.stats = stats;
+  const int64_t init_items = std::max<int64_t>(std::max<int64_t>(B, (int64_t)pl.cap), tq::C_INTS);
+  k_queue_init<<<(unsigned)((init_items + 255) / 256), 256, 0, s>>>(q, pl.nwarps);
+  LAUNCH_CHECK();
+  constexpr bool can_close = M <= 2;
+  if (can_close && qp == QP_CLOSED) k_queue_solve<KIND, N, M, (M <= 2 ? QP_CLOSED : QP_NEWTON)><<<pl.nwarps, 32, 0, s>>>(e->es, o, q);
+  else k_queue_solve<KIND, N, M, QP_NEWTON><<<pl.nwarps, 32, 0, s>>>(e->es, o, q);
+  LAUNCH_CHECK();
+  return TFMPC_OK;
+}
+
+}  // namespace
+
+// ticket counters are 32-bit and a problem takes at most a few hundred tickets: larger batches are solved in slices
+constexpr int64_t kMaxSlice = 1 << 21;
+
+int64_t queue_ilqr_workspace_bytes(const tfmpc_env *e, int64_t B, int T) { return make_plan(e, std::min(B, kMaxSlice), T).bytes; }
+
+int queue_ilqr_option(const char *name, int value, int *previous) {
+  std::atomic<int> *t = nullptr;
+  if (!strcmp(name, "queue_warps_per_sm")) t = &g_wps;
+  else if (!strcmp(name, "queue_w_target")) t = &g_w_target;
+  else if (!strcmp(name, "queue_patience")) t = &g_patience;
+  if (!t) return 0;
+  *previous = t->exchange(value);
+  return 1;
+}
+
+// control block of the last solve in this workspace (diagnostics: warp iterations, lanes, rounds, ...)
+int queue_ilqr_counters(const void *ws, int *out, int n, cudaStream_t s) {
+  CUDA_TRY(cudaMemcpyAsync(out, ws, sizeof(int) * std::min(n, (int)tq::C_INTS), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  return TFMPC_OK;
+}
+
+int queue_ilqr_solve(const tfmpc_env *e, int64_t B, int T, const real *x0, const real *u_init, const IlqrOpts &o, real *states,
+                     real *actions, real *costs, int32_t *stats, void *ws, int64_t ws_bytes, int qp, cudaStream_t s) {
+  if (ws_bytes < queue_ilqr_workspace_bytes(e, B, T)) return tfmpc_set_error(TFMPC_E_WORKSPACE, "workspace too small");
+  const int n = e->n, m = e->m;
+  for (int64_t off = 0; off < B; off += kMaxSlice) {   // slices run one after another in stream order and share the workspace
+    const int64_t Bs = std::min(kMaxSlice, B - off);
+    const real *x0s = x0 + off * n, *u0s = u_init + off * T * m;
+    real *ss = states + off * (T + 1) * n, *as = actions + off * T * m, *cs = costs + off * (T + 1);
+    int32_t *sts = stats + off * 4;
+    int rc;
+#define CALL(KD, N, M) rc = launch<KD, N, M>(e, Bs, T, x0s, u0s, o, ss, as, cs, sts, ws, qp, s)
+    if (e->kind == TFMPC_ENV_NAVIGATION && n == 2 && e->nz <= 2) CALL(TFMPC_ENV_NAVIGATION_Z2, 2, 2);
+    else if (e->kind == TFMPC_ENV_NAVIGATION && n == 2) CALL(TFMPC_ENV_NAVIGATION, 2, 2);
+    else if (e->kind == TFMPC_ENV_NAVLQR && n == 1) CALL(TFMPC_ENV_NAVLQR, 1, 1);
+    else if (e->kind == TFMPC_ENV_NAVLQR && n == 2) CALL(TFMPC_ENV_NAVLQR, 2, 2);
+    else if (e->kind == TFMPC_ENV_NAVLQR && n == 3) CALL(TFMPC_ENV_NAVLQR, 3, 3);
+    else if (e->kind == TFMPC_ENV_NAVLQR && n == 4) CALL(TFMPC_ENV_NAVLQR, 4, 4);
+    else return tfmpc_set_error(TFMPC_E_UNSUPPORTED, "no thread-per-problem kernel for kind=%d n=%d", e->kind, n);
+#undef CALL
+    if (rc) return rc;
+  }
+  return TFMPC_OK;
+}

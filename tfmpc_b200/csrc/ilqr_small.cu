@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(kThreads) k_init(EnvSmall e, int64_t B, int T,
 // COOP: warp-cooperative box-QP backtracking (bounded environments).  The loop is warp-uniform: lanes past the end of
 // the active list shadow the last active problem (same nominal, gains written to the spare slot S-1, no state written),
 // so that all 32 lanes stay in lock step through the cooperative phases.
-template <int KIND, int N, int M, bool COOP>
+template <int KIND, int N, int M, int QP>
 __global__ void __launch_bounds__(kThreads) k_tick_backward(EnvSmall e, IlqrOpts o, int T, WS w, int parity) {
   const int cnt = w.count[parity];
   if (blockIdx.x == 0 && threadIdx.x == 0) w.count[parity ^ 1] = 0;  // filled by this tick's line-search kernel
@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(kThreads) k_tick_backward(EnvSmall e, IlqrOpts
     const int64_t b = list[valid ? i : cnt - 1];
     Prob p;
     load_prob(w, b, p);
-    tick_backward<KIND, N, M, COOP>(e, o, T, buf_traj<N, M>(w, p.cur, b), buf_gain<N, M>(w, valid ? b : w.S - 1), p);
+    tick_backward<KIND, N, M, QP>(e, o, T, buf_traj<N, M>(w, p.cur, b), buf_gain<N, M>(w, valid ? b : w.S - 1), p);
     if (valid) {
       w.n_bwd[b] = p.n_bwd; w.status[b] = p.status; w.phase[b] = p.phase;
       w.J_hat[b] = p.J_hat; w.dV1[b] = p.dV1; w.dV2[b] = p.dV2;
@@ -572,8 +572,8 @@ static int solve_launch(const tfmpc_env *e, int64_t B, int T, const real *x0, co
   auto enqueue_ticks = [&](int t0, int t1, cudaStream_t q) {
     for (int t = t0; t < t1; t++) {
       const bool big = t < kHeadTicks;   // grid size follows the expected active count, whichever stream the tick runs on
-      if (e->bounded) k_tick_backward<KIND, N, M, true><<<big ? g_bwd : g_bwd_t, kThreads, 0, q>>>(e->es, o, T, w, t & 1);
-      else k_tick_backward<KIND, N, M, false><<<big ? g_bwd : g_bwd_t, kThreads, 0, q>>>(e->es, o, T, w, t & 1);
+      if (e->bounded) k_tick_backward<KIND, N, M, QP_COOP><<<big ? g_bwd : g_bwd_t, kThreads, 0, q>>>(e->es, o, T, w, t & 1);
+      else k_tick_backward<KIND, N, M, QP_NEWTON><<<big ? g_bwd : g_bwd_t, kThreads, 0, q>>>(e->es, o, T, w, t & 1);
       k_tick_linesearch<KIND, N, M><<<big ? g_ls : g_ls_t, kThreads, 0, q>>>(e->es, o, T, w, t & 1);
     }
   };

@@ -249,6 +249,26 @@ def ilqr_solve(env, x0, u_init, opts=None, out=None):
     return out
 
 
+def set_option(name, value, precision="f32"):
+    """tfmpc_set_option: runtime options of the small-environment solve ("solver": 1 queue / 0 ticks, "qp": 2 closed form /
+    0 the reference's projected-Newton iteration, "queue_warps_per_sm", "queue_w_target", "queue_patience").
+    Returns the previous value."""
+    lib = N.load(precision)
+    rc = lib.tfmpc_set_option(str(name).encode(), int(value))
+    if rc < 0:
+        N.check(lib, rc)
+    return int(rc)
+
+
+def queue_counters(workspace, precision="f32"):
+    """Scheduling counters the queue solver left in `workspace` (the tensor handed to the last solve; synchronises):
+    warp iterations, problem iterations, rollout rounds (search + store passes), store passes, watchdog flag."""
+    lib = N.load(precision)
+    out = (C.c_int32 * 5)()
+    N.check(lib, lib.tfmpc_ilqr_queue_counters(C.c_void_p(workspace.data_ptr()), out, N.stream_ptr()))
+    return dict(zip(("warp_iterations", "problem_iterations", "rounds", "store_passes", "watchdog"), [int(v) for v in out]))
+
+
 def set_graph_mode(on, precision="f32"):
     """tfmpc_set_graph_mode: CUDA-graph replay of repeated solves on the same buffers; returns the previous mode."""
     return bool(N.load(precision).tfmpc_set_graph_mode(int(bool(on))))

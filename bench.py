@@ -457,6 +457,13 @@ def run_ours(args):
     barrier()
     step_ms = [a.elapsed_time(b) for a, b in ev]
     seq_ms = float(sum(step_ms))
+    queue_counters = None
+    try:    # scheduling counters of the last sequential solve (queue solver only; the tick path leaves other data there)
+        ws_main = _native._WS_CACHE.get((dev, main.cuda_stream))
+        if ws_main is not None and args.workload == "c3" and os.environ.get("TFMPC_SOLVER", "queue") != "ticks":
+            queue_counters = ops.queue_counters(ws_main)
+    except Exception as exc:  # noqa: BLE001
+        queue_counters = {"error": str(exc)[:100]}
 
     # ---- (2) pipelined: the same K independent batches issued round-robin on S streams, so the latency-bound tail of
     #      one batch (few unconverged problems) overlaps the throughput-bound head of the next
@@ -632,6 +639,7 @@ def run_ours(args):
                 "per_rank": ({"columns": ["pipelined ms/step", "sequential ms/batch", "problem-iterations per batch", "final all-gather ms (incl. waiting for the slowest rank)", "host enqueue ms/step"], "ranks": per_rank}
                              if per_rank else None),
                 "host_enqueue_ms_per_step": issue_ms / args.steps,
+                "queue_counters": queue_counters,
                 "pipeline_timeline_ms": {"columns": ["stream", "start", "end"], "steps": timeline},
                 "roofline": roofline,
                 "e2e": {"value": e2e_value, "unit": "problem-iterations/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

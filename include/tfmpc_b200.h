@@ -214,14 +214,23 @@ int tfmpc_ilqr_solve(const tfmpc_env_t *env, int64_t B, int T, const tfmpc_real 
  *   "qp"                 box-QP of the constrained controller (ilqr.py:364-387) for m <= 2:
  *                        2 = closed form (default of the fp32 build), 0 = the reference's projected-Newton iteration
  *                        (optimization.py:6-101; default of the fp64 verification build)                        TFMPC_QP=closed|newton
- *   "queue_warps_per_sm" resident warps per SM of the queue kernel (default 16)                                  TFMPC_QUEUE_WPS
- *   "queue_w_target"     warps the queue plans its pop size for (0 = 8 per SM)                                   TFMPC_QUEUE_WTARGET
- *   "queue_patience"     idle polls before a warp takes fewer problems than planned                              TFMPC_QUEUE_PATIENCE */
+ *   "queue_warps_per_sm" resident warps per SM of the queue kernel (default 18)                                  TFMPC_QUEUE_WPS
+ *   "queue_w_target"     warps the queue plans its pop size for: a warp pops clamp(ceil(unfinished / w_target), 1, 32)
+ *                        problems (0 = one warp per SM: full warps until < 32 problems per SM are left; larger values
+ *                        spread the last problems over more, emptier warps: lower single-batch latency, lower throughput
+ *                        with several batches in flight)                                                         TFMPC_QUEUE_WTARGET
+ *   "queue_patience"     idle polls before a warp takes fewer problems than planned (default 0)                 TFMPC_QUEUE_PATIENCE
+ *   "queue_trace"        1 = record one scheduling-trace record per warp iteration (diagnostics)                 TFMPC_QUEUE_TRACE */
 int tfmpc_set_option(const char *name, int value);
 /* Diagnostics: copies the control block the queue solver left in `workspace` (after the solve has completed on `stream`):
  * out[0] = warp iterations, out[1] = problem iterations (lanes), out[2] = rollout rounds incl. store passes,
  * out[3] = store passes (problems), out[4] = watchdog flag.  Synchronises the stream. */
 int tfmpc_ilqr_queue_counters(const void *workspace, int32_t *out, void *stream);
+/* Diagnostics: the scheduling trace of the last solve of (env, B, T) in `workspace` (option "queue_trace" on): records of
+ * 4 uint32 = {acquire start (low 32 bits of the ns timer), ns waiting for tickets, ns working, lanes | rounds << 8 |
+ * warp slot << 16}.  Returns the number of records copied to `out` (HOST memory), or a negative error.  Synchronises. */
+int64_t tfmpc_ilqr_queue_trace(const tfmpc_env_t *env, int64_t B, int T, const void *workspace, uint32_t *out, int64_t max_records,
+                               void *stream);
 
 /* CUDA-graph replay of the tick solve's launch sequence (small environments): with on != 0 the second and later calls
  * with the same (environment, B, T, options, buffer addresses) replay two captured graphs instead of enqueueing 253

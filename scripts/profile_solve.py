@@ -12,12 +12,13 @@ from tfmpc_b200.solvers.ilqr import iLQR
 ap = argparse.ArgumentParser()
 ap.add_argument("--workload", default="c3")
 ap.add_argument("--batch", type=int, default=0)
+ap.add_argument("--max-iterations", type=int, default=100)
 a = ap.parse_args()
 desc, B, T = bench.WORKLOADS[a.workload]
 B = a.batch or B
 cfg = bench.workload_cfg(a.workload)
 env = envs.make_env(cfg)
-solver = iLQR(env)
+solver = iLQR(env, max_iterations=a.max_iterations)
 x0, u0 = bench.make_inputs(cfg, B, T, seed=1000)
 x0, u0 = torch.from_numpy(x0).cuda(), torch.from_numpy(u0).cuda()
 out = ops.ilqr_solve(env.native(), x0, u0, solver._opts())

@@ -34,7 +34,7 @@ static int run(const EnvSmall &e, const IlqrOpts &o, int B, int T, const real *x
                real *costs, int32_t *stats, int nwarps, int w_target, int patience, int *ctrl_out) {
   using namespace tq;
   constexpr int CHn = VecTraj<N, M>::CH;
-  const int NL = ((T + 1) * CHn + 7) / 8, row_r4 = NL * 8;
+  const int NH = ((T + 1) * CHn + CPH - 1) / CPH, row_r4 = NH * CPH;
   unsigned cap = 1024;
   while (cap < 2u * (unsigned)B) cap <<= 1;
   std::vector<int> ctrl(C_INTS, 0);
@@ -43,13 +43,14 @@ static int run(const EnvSmall &e, const IlqrOpts &o, int B, int T, const real *x
   std::vector<R4> traj((size_t)2 * B * row_r4);
   std::vector<R2> gain((size_t)nwarps * T * Gain2<N, M>::CH2 * 32);
   memset(traj.data(), 0xff, traj.size() * sizeof(R4));   // NaN pattern: any read of an unwritten record shows up
-  ctrl[C_TAIL] = B; ctrl[C_ALIVE] = nwarps;
+  ctrl[C_TAIL] = B; ctrl[C_COUNT] = B; ctrl[C_ALIVE] = nwarps;
   QParams q;
   q.ctrl = ctrl.data(); q.ring = ring.data(); q.ring_mask = cap - 1; q.prob = prob.data(); q.traj = traj.data(); q.gain = gain.data();
   q.B = B; q.T = T; q.row_r4 = row_r4; q.w_target = w_target; q.patience = patience; q.watchdog_ns = 120ull * 1000000000ull;
+  q.trace = nullptr; q.trace_cap = 0;
   q.x0 = x0; q.u_init = u_init; q.states = states; q.actions = actions; q.costs = costs; q.stats = stats;
   std::vector<WarpShared> shared(nwarps);
-  std::vector<WarpSmem> smem(nwarps);
+  std::vector<WarpSmem<N, M>> smem(nwarps);
   for (auto &w : shared) pthread_barrier_init(&w.bar, nullptr, 32);
   std::vector<std::thread> th;
   for (int w = 0; w < nwarps; w++)

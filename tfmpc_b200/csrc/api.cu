@@ -347,11 +347,16 @@ int tfmpc_set_option(const char *name, int value) {
 
 int tfmpc_ilqr_queue_counters(const void *workspace, int32_t *out, void *stream) {
   REQ(workspace && out, "tfmpc_ilqr_queue_counters: null argument");
-  int raw[320];
-  int rc = queue_ilqr_counters(workspace, raw, 320, (cudaStream_t)stream);
+  int raw[352];
+  int rc = queue_ilqr_counters(workspace, raw, 352, (cudaStream_t)stream);
   if (rc) return rc;
   out[0] = raw[160]; out[1] = raw[192]; out[2] = raw[224]; out[3] = raw[256]; out[4] = raw[128];
   return TFMPC_OK;
+}
+
+int64_t tfmpc_ilqr_queue_trace(const tfmpc_env_t *e, int64_t B, int T, const void *workspace, uint32_t *out, int64_t max_records, void *stream) {
+  if (!e || !workspace || !out || !use_small(e)) return tfmpc_set_error(TFMPC_E_INVALID, "tfmpc_ilqr_queue_trace: bad argument");
+  return queue_ilqr_trace(e, B, T, workspace, out, max_records, (cudaStream_t)stream);
 }
 
 int64_t tfmpc_ilqr_workspace_bytes(const tfmpc_env_t *e, int64_t B, int T) {

@@ -131,6 +131,7 @@ int queue_ilqr_solve(const tfmpc_env *e, int64_t B, int T, const real *x0, const
                      real *actions, real *costs, int32_t *stats, void *ws, int64_t ws_bytes, int qp, cudaStream_t s);
 int queue_ilqr_option(const char *name, int value, int *previous);
 int queue_ilqr_counters(const void *ws, int *out, int n, cudaStream_t s);
+int64_t queue_ilqr_trace(const tfmpc_env *e, int64_t B, int T, const void *ws, unsigned *out, int64_t max_records, cudaStream_t s);
 int small_boxqp(int64_t B, int m, const real *H, const real *q, const real *lo, const real *hi, real *x, real *Hfree, int32_t *isfree,
                 int32_t *nfree, int32_t *status, cudaStream_t s);
 

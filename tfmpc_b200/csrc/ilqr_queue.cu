@@ -9,22 +9,25 @@
 
 namespace {
 
-#ifdef TFMPC_F64
-constexpr int kMaxWarpsPerSM = 8;    // WarpSmem is 19 KB in the fp64 build
+#if defined(TFMPC_QUEUE_MAXWPS)
+constexpr int kMaxWarpsPerSM = TFMPC_QUEUE_MAXWPS;   // A/B builds (scripts/build_variant.py)
+#elif defined(TFMPC_F64)
+constexpr int kMaxWarpsPerSM = 8;    // WarpSmem is 23 KB in the fp64 build (n = m = 2)
 #else
-constexpr int kMaxWarpsPerSM = 16;   // 128 registers per thread
+constexpr int kMaxWarpsPerSM = 18;   // 11.8 KB of shared memory per warp (n = m = 2) and 96 registers per thread (no spills): measured
+                                     // 337 M problem-iterations/s against 306 at 16 warps / 106 registers (profiles/r02_ab_queue.txt)
 #endif
 
 template <int KIND, int N, int M, int QP>
 __global__ void __launch_bounds__(32, kMaxWarpsPerSM) k_queue_solve(EnvSmall e, IlqrOpts o, tq::QParams q) {
-  __shared__ tq::WarpSmem sm;
+  __shared__ tq::WarpSmem<N, M> sm;
   WarpRT rt;
   tq::queue_warp_main<KIND, N, M, QP>(rt, e, o, q, sm, (int)blockIdx.x);
 }
 
 __global__ void __launch_bounds__(256) k_queue_init(tq::QParams q, int nwarps) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < tq::C_INTS) q.ctrl[i] = i == tq::C_TAIL ? q.B : (i == tq::C_ALIVE ? nwarps : 0);
+  if (i < tq::C_INTS) q.ctrl[i] = (i == tq::C_TAIL || i == tq::C_COUNT) ? q.B : (i == tq::C_ALIVE ? nwarps : 0);
   if (i <= q.ring_mask) q.ring[i] = 0ull;   // ticket field 0 never matches a re-queue ticket (those are >= B >= 1)
   if (i < q.B) reinterpret_cast<int4 *>(q.stats)[i] = make_int4(0, 0, 0, TFMPC_ST_ABORTED);   // overwritten when the problem finishes
 }
@@ -35,8 +38,10 @@ int env_int(const char *name, int dflt) {
 }
 
 std::atomic<int> g_wps{env_int("TFMPC_QUEUE_WPS", kMaxWarpsPerSM)};
-std::atomic<int> g_w_target{env_int("TFMPC_QUEUE_WTARGET", 0)};   // 0 = 8 warps per SM
-std::atomic<int> g_patience{env_int("TFMPC_QUEUE_PATIENCE", 4)};
+std::atomic<int> g_w_target{env_int("TFMPC_QUEUE_WTARGET", 0)};   // 0 = one warp per SM
+std::atomic<int> g_patience{env_int("TFMPC_QUEUE_PATIENCE", 0)};
+std::atomic<int> g_trace{env_int("TFMPC_QUEUE_TRACE", 0)};
+constexpr int kTraceCap = 1 << 18;   // warp iterations recorded when the trace is on (4 MB)
 
 int device_sms(int device) {
   static int cached[64] = {0};
@@ -50,15 +55,15 @@ int device_sms(int device) {
 struct Plan {
   int nwarps, NL, row_r4, ch2;
   unsigned cap;
-  int64_t o_ctrl, o_ring, o_prob, o_traj, o_gain, bytes;
+  int64_t o_ctrl, o_ring, o_prob, o_traj, o_gain, o_trace, bytes;
 };
 
 Plan make_plan(const tfmpc_env *e, int64_t B, int T) {
   Plan p;
   const int n = e->n, m = e->m;
   const int chn = (n + m + 3) / 4;
-  p.NL = ((T + 1) * chn + 7) / 8;
-  p.row_r4 = p.NL * 8;
+  p.NL = ((T + 1) * chn + tq::CPH - 1) / tq::CPH;   // half-lines per trajectory row
+  p.row_r4 = p.NL * tq::CPH;
   p.ch2 = (m * n + m + 1) / 2;
   const int wps = std::max(1, std::min(g_wps.load(), kMaxWarpsPerSM));
   p.nwarps = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)device_sms(e->device) * wps, B));
@@ -71,6 +76,7 @@ Plan make_plan(const tfmpc_env *e, int64_t B, int T) {
   p.o_prob = off; off += al(B * (int64_t)sizeof(tq::QProb));
   p.o_traj = off; off += al(2 * B * p.row_r4 * (int64_t)sizeof(R4));
   p.o_gain = off; off += al((int64_t)p.nwarps * T * p.ch2 * 32 * (int64_t)sizeof(tq::R2));
+  p.o_trace = off; off += al((int64_t)kTraceCap * 16);
   p.bytes = off;
   return p;
 }
@@ -89,10 +95,12 @@ int launch(const tfmpc_env *e, int64_t B, int T, const real *x0, const real *u_i
   q.gain = (tq::R2 *)(base + pl.o_gain);
   q.B = (int)B; q.T = T; q.row_r4 = pl.row_r4;
   const int wt = g_w_target.load();
-  q.w_target = wt > 0 ? wt : device_sms(e->device) * 8;
+  q.w_target = wt > 0 ? wt : device_sms(e->device);
   q.patience = std::max(0, g_patience.load());
   q.watchdog_ns = 4000000000ull;   // 4 s without progress for one warp: give up (status TFMPC_ST_ABORTED) instead of hanging the device
   q.x0 = x0; q.u_init = u_init; q.states = states; q.actions = actions; q.costs = costs; q.stats = stats;
+  q.trace = g_trace.load() ? (unsigned *)(base + pl.o_trace) : nullptr;
+  q.trace_cap = kTraceCap;
   const int64_t init_items = std::max<int64_t>(std::max<int64_t>(B, (int64_t)pl.cap), tq::C_INTS);
   k_queue_init<<<(unsigned)((init_items + 255) / 256), 256, 0, s>>>(q, pl.nwarps);
   LAUNCH_CHECK();
@@ -115,6 +123,7 @@ int queue_ilqr_option(const char *name, int value, int *previous) {
   if (!strcmp(name, "queue_warps_per_sm")) t = &g_wps;
   else if (!strcmp(name, "queue_w_target")) t = &g_w_target;
   else if (!strcmp(name, "queue_patience")) t = &g_patience;
+  else if (!strcmp(name, "queue_trace")) t = &g_trace;
   if (!t) return 0;
   *previous = t->exchange(value);
   return 1;
@@ -125,6 +134,18 @@ int queue_ilqr_counters(const void *ws, int *out, int n, cudaStream_t s) {
   CUDA_TRY(cudaMemcpyAsync(out, ws, sizeof(int) * std::min(n, (int)tq::C_INTS), cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaStreamSynchronize(s));
   return TFMPC_OK;
+}
+
+// scheduling trace of the last solve in this workspace (option "queue_trace" must have been on): up to max_records records of 4 uint32
+int64_t queue_ilqr_trace(const tfmpc_env *e, int64_t B, int T, const void *ws, unsigned *out, int64_t max_records, cudaStream_t s) {
+  const Plan pl = make_plan(e, std::min(B, kMaxSlice), T);
+  int n = 0;
+  CUDA_TRY(cudaMemcpyAsync(&n, (const char *)ws + pl.o_ctrl + 4 * tq::C_TRACE, 4, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  int64_t cnt = std::min<int64_t>(std::min<int64_t>(n, kTraceCap), max_records);
+  if (cnt > 0) CUDA_TRY(cudaMemcpyAsync(out, (const char *)ws + pl.o_trace, cnt * 16, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  return cnt;
 }
 
 int queue_ilqr_solve(const tfmpc_env *e, int64_t B, int T, const real *x0, const real *u_init, const IlqrOpts &o, real *states,

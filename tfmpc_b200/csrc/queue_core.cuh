@@ -19,11 +19,12 @@
 // the queue empty retire (freeing their SM slots for the next batch's kernel), and near the end the pop size shrinks so
 // that the last stragglers each own a warp (all 11 step sizes in one round).
 //
-// Memory traffic.  Trajectories are PROBLEM-major (one problem = one contiguous, 128-byte aligned row) and move between
-// HBM/L2 and shared memory only as whole 128-byte lines: 8 lanes fetch one line with cp.async (4 lines per instruction
-// instead of 32 scattered sectors), the store pass overwrites the staged nominal records in place with the candidate, and
-// the same 8-lane pattern writes the line back.  Gains never leave the warp: [warp][t][chunk][lane] scratch, written and
-// read back (coalesced) within the same warp iteration, i.e. L2-resident.
+// Memory traffic.  Trajectories are PROBLEM-major (one problem = one contiguous, 64-byte aligned row) and move between
+// HBM/L2 and shared memory only as 64-byte half-lines (4 steps for n = m = 2): 4 lanes fetch one half-line with cp.async
+// (8 rows per instruction instead of 32 scattered sectors), the store pass overwrites the staged nominal records in place
+// with the candidate, and the same 4-lane pattern writes the half-line back.  Gains never leave the warp:
+// [warp][t][pair][lane] scratch written by the backward sweep and streamed back by the rollouts, again with cp.async, one
+// contiguous block per half-line of steps.  Everything a rollout consumes is requested 4-8 steps ahead of its use.
 #pragma once
 #include "small_core.cuh"
 #include "warp_rt.cuh"
@@ -31,7 +32,7 @@
 namespace tq {
 
 // control block (ints, one counter per 128-byte line)
-enum { C_HEAD = 0, C_TAIL = 32, C_DONE = 64, C_ALIVE = 96, C_ERR = 128, C_WITER = 160, C_LANES = 192, C_ROUNDS = 224, C_REPLAYS = 256, C_BWD = 288, C_INTS = 320 };
+enum { C_HEAD = 0, C_TAIL = 32, C_DONE = 64, C_ALIVE = 96, C_ERR = 128, C_WITER = 160, C_LANES = 192, C_ROUNDS = 224, C_REPLAYS = 256, C_COUNT = 288, C_TRACE = 320, C_INTS = 352 };
 
 struct alignas(16) QProb {   // per-problem solver state carried between iterations (one 32-byte sector)
   double mu, delta;
@@ -54,12 +55,19 @@ struct QParams {
   const real *x0, *u_init;
   real *states, *actions, *costs;
   int32_t *stats;
+  // optional scheduling trace (diagnostics, option "queue_trace"): one record per warp iteration
+  //   {acquire start [ns, low 32 bits of %globaltimer], wait for tickets [ns], work [ns], lanes | rounds << 8 | warp slot << 16}
+  unsigned *trace;
+  int trace_cap;
 };
 
-struct WarpSmem {
-  R4 buf[2][32][9];             // two line buffers: [row = lane of the owning problem][8 chunks + 1 pad (bank spread)]
+constexpr int CPH = 4;         // 16-byte chunks (R4) per staged half-line of a trajectory row
+template <int GAIN_HALF_R2>    // R2 elements of one staged half-line of gains: steps per half-line * Gain2::CH2 * 32
+struct WarpSmemT {
+  R4 buf[2][32][CPH + 1];       // two half-line buffers: [row = lane of the owning problem][4 chunks + 1 pad (bank spread)]
   const R4 *inrow[32];          // nominal trajectory row of each lane's problem
   R4 *outrow[32];               // candidate trajectory row (the problem's other buffer)
+  R2 gbuf[2][GAIN_HALF_R2];     // rollouts: gains of two half-lines of steps, [step][pair][lane] as in the scratch
 };
 
 HD int popc32(unsigned m) {
@@ -83,15 +91,42 @@ HD R4 *traj_row(const QParams &q, int buf, int b) { return q.traj + ((int64_t)bu
 // Gains (K_t, k_t) of the problem held by one lane: per-warp scratch [t][pair][lane] in 2-real units, so a warp's store
 // or load of one pair is a single contiguous 256-byte (fp32) row and a problem-step costs M*N+M reals with no padding
 // (24 bytes for n = m = 2).  `base` already points at the lane's column.
+// L2 residency hint (TFMPC_QUEUE_L2HINT, fp32 build): gain accesses carry an evict_last policy so that the scratch a warp
+// re-reads within the same iteration outlives the streaming trajectory lines in the 126 MB L2.
+#if defined(__CUDA_ARCH__) && defined(TFMPC_QUEUE_L2HINT) && !defined(TFMPC_F64)
+#define TQ_GAIN_HINT 1
+__device__ __forceinline__ unsigned long long tq_policy_evict_last() {
+  unsigned long long p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;\n" : "=l"(p));
+  return p;
+}
+#endif
+
 template <int N, int M>
 struct Gain2 {
   static constexpr int G = M * N + M, CH2 = (G + 1) / 2;
   R2 *base;
+  HD R2 ld(const R2 *p) const {
+#ifdef TQ_GAIN_HINT
+    R2 v;
+    asm volatile("ld.global.L2::cache_hint.v2.f32 {%0, %1}, [%2], %3;\n" : "=f"(v.v[0]), "=f"(v.v[1]) : "l"(p), "l"(tq_policy_evict_last()));
+    return v;
+#else
+    return *p;
+#endif
+  }
+  HD void st(R2 *p, const R2 &v) const {
+#ifdef TQ_GAIN_HINT
+    asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1, %2}, %3;\n" ::"l"(p), "f"(v.v[0]), "f"(v.v[1]), "l"(tq_policy_evict_last()) : "memory");
+#else
+    *p = v;
+#endif
+  }
   HD void load(int t, real *Kt, real *kt) const {
     real r[2 * CH2];
 #pragma unroll
     for (int c = 0; c < CH2; c++) {
-      const R2 v = base[((int64_t)t * CH2 + c) * 32];
+      const R2 v = ld(base + ((int64_t)t * CH2 + c) * 32);
       r[2 * c] = v.v[0]; r[2 * c + 1] = v.v[1];
     }
 #pragma unroll
@@ -111,32 +146,34 @@ struct Gain2 {
     for (int c = 0; c < CH2; c++) {
       R2 v;
       v.v[0] = r[2 * c]; v.v[1] = r[2 * c + 1];
-      base[((int64_t)t * CH2 + c) * 32] = v;
+      st(base + ((int64_t)t * CH2 + c) * 32, v);
     }
   }
 };
 
-// ---- cooperative line staging: lanes 8i..8i+7 move the 8 chunks of one row's line, 4 rows per instruction
-WD void fetch_line(WarpRT &rt, WarpSmem &sm, int p, int line, int NL, unsigned rows) {
-  if (line >= 0 && line < NL) {
+// ---- cooperative half-line staging: lanes 4i..4i+3 move the 4 chunks of one row's half-line, 8 rows per instruction.
+// The fetches only ISSUE the copies; the caller closes a group with cp_commit().
+template <class WarpSmem>
+WD void fetch_half(WarpRT &rt, WarpSmem &sm, int p, int h, int NH, unsigned rows) {
+  if (h >= 0 && h < NH) {
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
-      const int row = 4 * i + (rt.lane >> 3), c = rt.lane & 7;
+    for (int i = 0; i < 4; i++) {
+      const int row = 8 * i + (rt.lane >> 2), c = rt.lane & 3;
       if ((rows >> row) & 1u) {
-        const char *src = (const char *)(sm.inrow[row] + line * 8 + c);
+        const char *src = (const char *)(sm.inrow[row] + h * CPH + c);
         char *dst = (char *)&sm.buf[p][row][c];
 #pragma unroll
         for (int o = 0; o < (int)sizeof(R4); o += 16) rt.cp_async16(dst + o, src + o);   // one chunk: 16 bytes (fp32) / 32 bytes (fp64 build)
       }
     }
   }
-  rt.cp_commit();   // one group per call on every lane, empty or not, so that wait_group counts lines
 }
-WD void writeout_line(WarpRT &rt, WarpSmem &sm, int p, int line, unsigned rows) {
+template <class WarpSmem>
+WD void writeout_half(WarpRT &rt, WarpSmem &sm, int p, int h, unsigned rows) {
 #pragma unroll
-  for (int i = 0; i < 8; i++) {
-    const int row = 4 * i + (rt.lane >> 3), c = rt.lane & 7;
-    if ((rows >> row) & 1u) sm.outrow[row][line * 8 + c] = sm.buf[p][row][c];
+  for (int i = 0; i < 4; i++) {
+    const int row = 8 * i + (rt.lane >> 2), c = rt.lane & 3;
+    if ((rows >> row) & 1u) sm.outrow[row][h * CPH + c] = sm.buf[p][row][c];
   }
 }
 
@@ -152,30 +189,32 @@ struct SlotOut {   // forward_step's trajectory sink: overwrite the staged recor
   }
 };
 
-// ---- iLQR.backward (ilqr.py:94-172) + derivatives (:84-92) for the lanes with `act`, nominal streamed last line first.
-// Every lane of the warp calls this (the staging is cooperative).  Returns backward_pass()'s status for `act` lanes.
-template <int KIND, int N, int M, int QP>
-WD int backward_staged(WarpRT &rt, WarpSmem &sm, const EnvSmall &e, int T, int NL, bool act, real mu, R2 *gain_lane, real &J, real &dV1,
+// ---- iLQR.backward (ilqr.py:94-172) + derivatives (:84-92) for the lanes with `act`, nominal streamed last half-line
+// first.  Every lane of the warp calls this (the staging is cooperative).  Returns backward_pass()'s status for `act` lanes.
+template <int KIND, int N, int M, int QP, class WarpSmem>
+WD int backward_staged(WarpRT &rt, WarpSmem &sm, const EnvSmall &e, int T, int NH, bool act, real mu, R2 *gain_lane, real &J, real &dV1,
                        real &dV2, real &gsum) {
-  constexpr int CHn = VecTraj<N, M>::CH, RPL = 8 / CHn;
+  constexpr int CHn = VecTraj<N, M>::CH, HS = CPH / CHn;   // records per half-line
   const unsigned rows = rt.ballot(act);
   const Gain2<N, M> gain = {gain_lane};
-  fetch_line(rt, sm, (NL - 1) & 1, NL - 1, NL, rows);
-  fetch_line(rt, sm, (NL - 2) & 1, NL - 2, NL, rows);
+  fetch_half(rt, sm, (NH - 1) & 1, NH - 1, NH, rows);
+  rt.cp_commit();
+  fetch_half(rt, sm, (NH - 2) & 1, NH - 2, NH, rows);
+  rt.cp_commit();
   real V_x[N], V_xx[N * N];
   int status = 0;
   bool live = act;
   J = 0; dV1 = 0; dV2 = 0; gsum = 0;
-  for (int l = NL - 1; l >= 0; l--) {
+  for (int h = NH - 1; h >= 0; h--) {
     rt.template cp_wait<1>();
     rt.syncwarp();
     if (live) {
 #pragma unroll 1
-      for (int s = RPL - 1; s >= 0; s--) {
-        const int t = l * RPL + s;
+      for (int s = HS - 1; s >= 0; s--) {
+        const int t = h * HS + s;
         if (t > T || !live) continue;
         real x[N], u[M];
-        VecTraj<N, M>{&sm.buf[l & 1][rt.lane][s * CHn], 0, 1}.load_xu(0, x, u);
+        VecTraj<N, M>{&sm.buf[h & 1][rt.lane][s * CHn], 0, 1}.load_xu(0, x, u);
         if (t == T) {
           env_final_quad<KIND, N, M>(e, x, J, V_x, V_xx);  // :101-104
           continue;
@@ -197,7 +236,8 @@ WD int backward_staged(WarpRT &rt, WarpSmem &sm, const EnvSmall &e, int T, int N
       }
     }
     rt.syncwarp();
-    fetch_line(rt, sm, l & 1, l - 2, NL, rows);
+    fetch_half(rt, sm, h & 1, h - 2, NH, rows);
+    rt.cp_commit();
   }
   rt.template cp_wait<0>();
   return status;
@@ -206,57 +246,92 @@ WD int backward_staged(WarpRT &rt, WarpSmem &sm, const EnvSmall &e, int T, int N
 // ---- one line-search round: up to 32 concurrent rollouts (iLQR.forward, ilqr.py:174-212).  Lane = (problem of lane
 // `src`, step size alpha); `rows` = lanes whose problem takes part.  STORE = false: search round, only J and the
 // residual are produced.  STORE = true: store pass (src == lane): the candidate overwrites the staged nominal records in
-// place and every line is written to the problem's other trajectory buffer.
-template <int KIND, int N, int M, bool STORE>
-WD void rollout_round(WarpRT &rt, WarpSmem &sm, const EnvSmall &e, int T, int NL, unsigned rows, int src, bool run, real alpha,
-                      const R2 *gain_src, real &J, real &residual) {
-  constexpr int CHn = VecTraj<N, M>::CH, RPL = 8 / CHn;
-  static_assert(RPL % 2 == 0, "records per line must be even (gain double buffer)");
+// place and every half-line is written to the problem's other trajectory buffer.
+// Gains are staged like the nominal: the warp's scratch is [step][pair][lane], so the gains of one half-line of steps are
+// one contiguous block that the 32 lanes copy together.  cp.async group H(h) = {nominal half-line h of every row, gains of
+// its steps}, issued two half-lines ahead (the 126 MB L2 does not hold the ~190 MB of gains and trajectories in flight, so
+// most of these reads come from HBM: with gains loaded into registers one step ahead, 45 % of the rollouts' stall samples
+// were the first use of a gain -- ncu, bulk phase).
+template <int N, int M>
+struct GainStage {
+  static constexpr int CH2 = Gain2<N, M>::CH2, HS = CPH / VecTraj<N, M>::CH, HALF_R2 = HS * CH2 * 32;
+  static constexpr int HALF_BYTES = HALF_R2 * (int)sizeof(R2), STEP_BYTES = CH2 * 32 * (int)sizeof(R2);
+};
+template <int N, int M, class WarpSmem>
+WD void fetch_gain_half(WarpRT &rt, WarpSmem &sm, const R2 *gain_warp, int h, int T) {
+  typedef GainStage<N, M> GS;
+  const int t0 = h * GS::HS;
+  if (t0 < T) {
+    const char *src = (const char *)(gain_warp + (int64_t)t0 * GS::CH2 * 32);
+    char *dst = (char *)sm.gbuf[h & 1];
+    const int valid_bytes = (T - t0 < GS::HS ? T - t0 : GS::HS) * GS::STEP_BYTES;
+#pragma unroll
+    for (int o = 0; o < GS::HALF_BYTES; o += 32 * 16) {
+      const int off = o + rt.lane * 16;
+      if (off < valid_bytes) rt.cp_async16(dst + off, src + off);
+    }
+  }
+}
+
+template <int KIND, int N, int M, bool STORE, class WarpSmem>
+WD void rollout_round(WarpRT &rt, WarpSmem &sm, const EnvSmall &e, int T, int NH, unsigned rows, int src, bool run, real alpha,
+                      const R2 *gain_warp, real &J, real &residual) {
+  typedef GainStage<N, M> GS;
+  constexpr int CHn = VecTraj<N, M>::CH, HS = GS::HS;
   const CostSink none = {nullptr, 0};
-  const Gain2<N, M> gain = {const_cast<R2 *>(gain_src)};
-  fetch_line(rt, sm, 0, 0, NL, rows);
-  fetch_line(rt, sm, 1, 1, NL, rows);
+#pragma unroll
+  for (int h = 0; h < 2; h++) {
+    fetch_half(rt, sm, h, h, NH, rows);
+    fetch_gain_half<N, M>(rt, sm, gain_warp, h, T);
+    rt.cp_commit();
+  }
   real x[N];
 #pragma unroll
   for (int i = 0; i < N; i++) x[i] = 0;
-  NomRec<N, M> ra, rb;   // gains are fetched one step ahead into the record that is not in use (even / odd steps)
   J = 0; residual = 0;
-  if (run) gain.load(0, ra.K, ra.k);
-  auto step = [&](int t, NomRec<N, M> &use, NomRec<N, M> &nxt, R4 *rec) {
-    if (!run || t > T) return;
-    if (t < T) {
-      if (t + 1 < T) gain.load(t + 1, nxt.K, nxt.k);
-      VecTraj<N, M>{rec, 0, 1}.load_xu(0, use.xh, use.uh);
-      if (t == 0) {
-#pragma unroll
-        for (int i = 0; i < N; i++) x[i] = use.xh[i];
-      }
-      forward_step<KIND, N, M>(e, alpha, use, t, x, SlotOut<N, M>{rec, STORE}, none, J, residual);
-    } else {
-      SlotOut<N, M>{rec, STORE}.store_x(T, x);
-      J += env_final_cost<KIND, N, M>(e, x);
-    }
-  };
-  for (int l = 0; l < NL; l++) {
-    rt.template cp_wait<1>();
+  for (int h = 0; h < NH; h++) {
+    rt.template cp_wait<1>();   // H(h) has landed (H(h+1) may still be in flight)
     rt.syncwarp();
-    R4 *line = &sm.buf[l & 1][src][0];
-#pragma unroll 1   // code size: the 16 warps of an SM sit in different phases and share one instruction cache
-    for (int s = 0; s < RPL; s += 2) {
-      step(l * RPL + s, ra, rb, line + s * CHn);
-      step(l * RPL + s + 1, rb, ra, line + (s + 1) * CHn);
+    if (run) {
+      const Gain2<N, M> gain = {sm.gbuf[h & 1] + src};
+      R4 *half = &sm.buf[h & 1][src][0];
+#pragma unroll 1   // code size: the warps of an SM sit in different phases and share one instruction cache
+      for (int s = 0; s < HS; s++) {
+        const int t = h * HS + s;
+        if (t > T) continue;
+        R4 *rec = half + s * CHn;
+        if (t < T) {
+          NomRec<N, M> use;
+          gain.load(s, use.K, use.k);
+          VecTraj<N, M>{rec, 0, 1}.load_xu(0, use.xh, use.uh);
+          if (t == 0) {
+#pragma unroll
+            for (int i = 0; i < N; i++) x[i] = use.xh[i];
+          }
+          forward_step<KIND, N, M>(e, alpha, use, t, x, SlotOut<N, M>{rec, STORE}, none, J, residual);
+        } else {
+          SlotOut<N, M>{rec, STORE}.store_x(T, x);
+          J += env_final_cost<KIND, N, M>(e, x);
+        }
+      }
     }
     rt.syncwarp();
     if (STORE) {
-      writeout_line(rt, sm, l & 1, l, rows);
+      writeout_half(rt, sm, h & 1, h, rows);
       rt.syncwarp();
     }
-    fetch_line(rt, sm, l & 1, l + 2, NL, rows);
+    fetch_half(rt, sm, h & 1, h + 2, NH, rows);
+    fetch_gain_half<N, M>(rt, sm, gain_warp, h + 2, T);
+    rt.cp_commit();
   }
   rt.template cp_wait<0>();
 }
 
-// ---- queue: lane 0 claims `take` consecutive tickets starting at h (0 = this warp retires)
+// ---- queue: lane 0 claims `take` consecutive tickets starting at h (0 = this warp retires).
+// C_COUNT is a semaphore of queued tickets: a claim is one atomic subtraction (over-draws are handed back), then one
+// atomic add on C_HEAD numbers the tickets.  No compare-and-swap loop: with ~2,400 warps popping every ~100 us an
+// optimistic read-then-CAS never sees an unchanged head (measured: 60 ms per batch instead of 5).  A ticket may be numbered
+// before its producer has published it (the credit came from a later producer); the consumer then spins on the slot tag.
 WD int q_acquire(WarpRT &rt, const QParams &q, int &h_out) {
   int *ctrl = q.ctrl;
   unsigned long long t_start = 0;
@@ -264,18 +339,22 @@ WD int q_acquire(WarpRT &rt, const QParams &q, int &h_out) {
   int idle = 0;
   for (;;) {
     if (rt.ld_relaxed(ctrl + C_ERR)) return 0;
-    const int P = q.B - rt.ld_acquire(ctrl + C_DONE);   // problems not finished yet
+    const int P = q.B - rt.ld_relaxed(ctrl + C_DONE);   // problems not finished yet
     if (P <= 0) return 0;
-    const int h = rt.ld_relaxed(ctrl + C_HEAD), t = rt.ld_relaxed(ctrl + C_TAIL);
-    const int avail = t - h;
     int g = (P + q.w_target - 1) / q.w_target;
     g = g < 1 ? 1 : (g > 32 ? 32 : g);
-    if (avail >= g || (avail > 0 && idle >= q.patience)) {
-      const int take = avail < g ? avail : g;
-      if (rt.atomic_cas(ctrl + C_HEAD, h, h + take) == h) { h_out = h; return take; }
-      continue;
-    }
-    if (avail <= 0) {   // nothing queued (everything outstanding is being worked on): is this warp still needed?
+    const int avail = rt.ld_relaxed(ctrl + C_COUNT);
+    const bool settle = idle >= q.patience;   // waited long enough: take whatever is there
+    if (avail >= g || (avail > 0 && settle)) {
+      const int c = rt.atomic_add(ctrl + C_COUNT, -g);
+      const int take = c >= g ? g : (c > 0 ? c : 0);
+      if (take == g || (take > 0 && settle)) {
+        if (take < g) rt.atomic_add(ctrl + C_COUNT, g - take);
+        h_out = rt.atomic_add(ctrl + C_HEAD, take);
+        return take;
+      }
+      rt.atomic_add(ctrl + C_COUNT, g);   // not enough yet: hand everything back and wait
+    } else if (avail <= 0) {   // nothing queued (everything outstanding is being worked on): is this warp still needed?
       const int want = (P + g - 1) / g;
       if (rt.ld_relaxed(ctrl + C_ALIVE) > want) {
         if (rt.atomic_add(ctrl + C_ALIVE, -1) > want) return 0;   // retired
@@ -292,17 +371,24 @@ WD int q_acquire(WarpRT &rt, const QParams &q, int &h_out) {
 }
 
 // ---- the warp's main loop
+template <int N, int M>
+using WarpSmem = WarpSmemT<GainStage<N, M>::HALF_R2>;
+
 template <int KIND, int N, int M, int QP>
-WD void queue_warp_main(WarpRT &rt, const EnvSmall &e, const IlqrOpts &o, const QParams &q, WarpSmem &sm, int warp_slot) {
+WD void queue_warp_main(WarpRT &rt, const EnvSmall &e, const IlqrOpts &o, const QParams &q, WarpSmem<N, M> &sm, int warp_slot) {
   constexpr int CHn = VecTraj<N, M>::CH;
   static_assert(CHn == 1 || CHn == 2, "trajectory records are 1 or 2 chunks");
-  const int lane = rt.lane, T = q.T, B = q.B, NL = q.row_r4 / 8;
+  const int lane = rt.lane, T = q.T, B = q.B, NH = q.row_r4 / CPH;
   const CostSink none = {nullptr, 0};
   R2 *gain_ws = q.gain + (int64_t)warp_slot * T * Gain2<N, M>::CH2 * 32;
+  int n_witer = 0, n_lanes = 0, n_rounds = 0, n_stores = 0;   // scheduling statistics of this warp (flushed once, at exit)
   for (;;) {
     // ------------------------------------------------ acquire
     int h = 0, take = 0;
+    unsigned long long tr0 = 0, tr1 = 0;
+    if (q.trace && lane == 0) tr0 = rt.now_ns();
     if (lane == 0) take = q_acquire(rt, q, h);
+    if (q.trace && lane == 0) tr1 = rt.now_ns();
     take = rt.shfl(take, 0);
     h = rt.shfl(h, 0);
     if (take <= 0) break;
@@ -352,7 +438,7 @@ WD void queue_warp_main(WarpRT &rt, const EnvSmall &e, const IlqrOpts &o, const 
       real gsum = 0;
       while (rt.any(need_pass)) {
         real J, d1, d2, gs;
-        const int st = backward_staged<KIND, N, M, QP>(rt, sm, e, T, NL, need_pass, (real)mu_l, gain_ws + lane, J, d1, d2, gs);
+        const int st = backward_staged<KIND, N, M, QP>(rt, sm, e, T, NH, need_pass, (real)mu_l, gain_ws + lane, J, d1, d2, gs);
         if (need_pass) {
           p.n_bwd++;
           bst = st; p.J_hat = J; p.dV1 = d1; p.dV2 = d2; gsum = gs;
@@ -391,7 +477,7 @@ WD void queue_warp_main(WarpRT &rt, const EnvSmall &e, const IlqrOpts &o, const 
       const int first = rt.shfl(next_ai, src), cnt = rt.shfl(my_cnt, src);
       const bool run = in_group && a < cnt;
       real J = 0, res = 0;
-      rollout_round<KIND, N, M, false>(rt, sm, e, T, NL, act_mask, src, run, o.alphas[run ? first + a : 0], gain_ws + src, J, res);
+      rollout_round<KIND, N, M, false>(rt, sm, e, T, NH, act_mask, src, run, o.alphas[run ? first + a : 0], gain_ws, J, res);
       // each owner reads the results of its group in step-size order: first accept wins (:322-353)
       const bool owner = (act_mask >> lane) & 1u;
       const int base = owner ? popc32(act_mask & ((1u << lane) - 1u)) * per : 0;
@@ -418,7 +504,7 @@ WD void queue_warp_main(WarpRT &rt, const EnvSmall &e, const IlqrOpts &o, const 
     const unsigned take_mask = rt.ballot(take_cand);
     if (take_mask) {
       real J, res;
-      rollout_round<KIND, N, M, true>(rt, sm, e, T, NL, take_mask, lane, take_cand, o.alphas[take_cand ? chosen : 0], gain_ws + lane, J, res);
+      rollout_round<KIND, N, M, true>(rt, sm, e, T, NH, take_mask, lane, take_cand, o.alphas[take_cand ? chosen : 0], gain_ws, J, res);
       nrounds++;
     }
     if (valid && p.phase == PH_SEARCH && tick_finish(o, accept, residual, rollouts, p)) p.cur ^= 1;   // ilqr.py:253-270
@@ -458,16 +544,29 @@ WD void queue_warp_main(WarpRT &rt, const EnvSmall &e, const IlqrOpts &o, const 
     if (lane == 0) {
       if (km) t0 = rt.atomic_add(q.ctrl + C_TAIL, popc32(km));
       if (dm) rt.atomic_add(q.ctrl + C_DONE, popc32(dm));
-      rt.atomic_add(q.ctrl + C_WITER, 1);
-      rt.atomic_add(q.ctrl + C_LANES, take);
-      rt.atomic_add(q.ctrl + C_ROUNDS, nrounds);
-      rt.atomic_add(q.ctrl + C_REPLAYS, popc32(take_mask));
     }
     t0 = rt.shfl(t0, 0);
     if (keep) {
       const unsigned ticket = (unsigned)t0 + (unsigned)popc32(km & ((1u << lane) - 1u));
       rt.st_release64(q.ring + ((ticket - (unsigned)B) & q.ring_mask), ((unsigned long long)ticket << 32) | (unsigned)b);
     }
+    rt.syncwarp();
+    if (lane == 0 && km) rt.atomic_add(q.ctrl + C_COUNT, popc32(km));   // credit the semaphore once the tickets are published
+    n_witer++; n_lanes += take; n_rounds += nrounds; n_stores += popc32(take_mask);
+    if (q.trace && lane == 0) {
+      const int slot = rt.atomic_add(q.ctrl + C_TRACE, 1);
+      if (slot < q.trace_cap) {
+        unsigned *r = q.trace + (int64_t)slot * 4;
+        r[0] = (unsigned)tr0; r[1] = (unsigned)(tr1 - tr0); r[2] = (unsigned)(rt.now_ns() - tr1);
+        r[3] = (unsigned)take | ((unsigned)nrounds << 8) | ((unsigned)warp_slot << 16);
+      }
+    }
+  }
+  if (lane == 0) {
+    rt.atomic_add(q.ctrl + C_WITER, n_witer);
+    rt.atomic_add(q.ctrl + C_LANES, n_lanes);
+    rt.atomic_add(q.ctrl + C_ROUNDS, n_rounds);
+    rt.atomic_add(q.ctrl + C_REPLAYS, n_stores);
   }
 }
 

@@ -47,7 +47,7 @@ struct WarpRT {
   WD void st_release64(unsigned long long *p, unsigned long long v) const {
     asm volatile("st.release.gpu.global.u64 [%0], %1;\n" ::"l"(p), "l"(v) : "memory");
   }
-  WD void fence() const { __threadfence(); }
+  WD void fence() const { asm volatile("fence.acq_rel.gpu;\n" ::: "memory"); }
   WD void sleep_ns(unsigned ns) const { __nanosleep(ns); }
   WD unsigned long long now_ns() const {
     unsigned long long t;

@@ -269,6 +269,18 @@ def queue_counters(workspace, precision="f32"):
     return dict(zip(("warp_iterations", "problem_iterations", "rounds", "store_passes", "watchdog"), [int(v) for v in out]))
 
 
+def queue_trace(env, B, T, workspace, max_records=1 << 18):
+    """tfmpc_ilqr_queue_trace -> int64 array [records, 4] (acquire start ns (low 32 bits), wait ns, work ns, packed lanes/rounds/warp)."""
+    import numpy as np
+    out = np.zeros((max_records, 4), dtype=np.uint32)
+    env.lib.tfmpc_ilqr_queue_trace.restype = C.c_int64
+    n = env.lib.tfmpc_ilqr_queue_trace(env.handle, C.c_int64(B), int(T), C.c_void_p(workspace.data_ptr()), out.ctypes.data_as(C.c_void_p),
+                                       C.c_int64(max_records), N.stream_ptr())
+    if n < 0:
+        N.check(env.lib, int(n))
+    return out[: int(n)].astype(np.int64)
+
+
 def set_graph_mode(on, precision="f32"):
     """tfmpc_set_graph_mode: CUDA-graph replay of repeated solves on the same buffers; returns the previous mode."""
     return bool(N.load(precision).tfmpc_set_graph_mode(int(bool(on))))

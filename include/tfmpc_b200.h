@@ -251,6 +251,15 @@ int tfmpc_ilqr_solve_async(const tfmpc_env_t *env, int64_t B, int T, const tfmpc
 int tfmpc_ilqr_solve_host(tfmpc_env_t *env, int64_t B, int T, const tfmpc_real *x0, const tfmpc_real *u_init,
                           const tfmpc_ilqr_opts_t *opts, tfmpc_real *states, tfmpc_real *actions, tfmpc_real *costs,
                           int32_t *stats, void *stream);
+/* The same, without the synchronisation, for callers that keep several batches in flight from ONE host thread: the
+ * host->device copies, the solve and the device->host copies are enqueued on `stream` and the call returns (with PINNED
+ * host buffers the copies are truly asynchronous; pageable buffers make them synchronous, as with cudaMemcpyAsync).
+ * `scratch` is caller-owned device memory of at least tfmpc_ilqr_solve_host_scratch_bytes() bytes (256-byte aligned) that
+ * must not be shared by calls in flight on different streams.  Results are valid once `stream` has reached this point. */
+int64_t tfmpc_ilqr_solve_host_scratch_bytes(const tfmpc_env_t *env, int64_t B, int T);
+int tfmpc_ilqr_solve_host_async(const tfmpc_env_t *env, int64_t B, int T, const tfmpc_real *x0, const tfmpc_real *u_init,
+                                const tfmpc_ilqr_opts_t *opts, tfmpc_real *states, tfmpc_real *actions, tfmpc_real *costs,
+                                int32_t *stats, void *scratch, int64_t scratch_bytes, void *stream);
 int tfmpc_lqr_solve_host(int64_t B, int n, int m, int T, const tfmpc_real *F, int64_t sF, const tfmpc_real *f, int64_t sf,
                          const tfmpc_real *C, int64_t sC, const tfmpc_real *c, int64_t sc, const tfmpc_real *x0,
                          int terminal_zero, tfmpc_real *states, tfmpc_real *actions, tfmpc_real *costs, int32_t *status,

@@ -444,6 +444,47 @@ int tfmpc_ilqr_solve_host(tfmpc_env_t *e, int64_t B, int T, const real *x0, cons
   return TFMPC_OK;
 }
 
+int64_t tfmpc_ilqr_solve_host_scratch_bytes(const tfmpc_env_t *e, int64_t B, int T) {
+  if (!e || B < 0 || T < 1) return tfmpc_set_error(TFMPC_E_INVALID, "tfmpc_ilqr_solve_host_scratch_bytes: bad argument");
+  const int64_t n = e->n, m = e->m;
+  const int64_t ws = tfmpc_ilqr_workspace_bytes(e, B, T);
+  if (ws < 0) return ws;
+  return al(B * n * sizeof(real)) + 2 * al(B * T * m * sizeof(real)) + al(B * (T + 1) * n * sizeof(real)) + al(B * (T + 1) * sizeof(real)) +
+         al(B * 4 * sizeof(int32_t)) + ws;
+}
+
+int tfmpc_ilqr_solve_host_async(const tfmpc_env_t *e, int64_t B, int T, const real *x0, const real *u_init, const tfmpc_ilqr_opts_t *opts,
+                                real *states, real *actions, real *costs, int32_t *stats, void *scratch, int64_t scratch_bytes, void *stream) {
+  REQ(e && x0 && u_init && states && actions && costs && stats && B >= 0 && T >= 1, "tfmpc_ilqr_solve_host_async: bad argument");
+  if (B == 0) return TFMPC_OK;
+  REQ(scratch, "tfmpc_ilqr_solve_host_async: null scratch");
+  const int64_t need = tfmpc_ilqr_solve_host_scratch_bytes(e, B, T);
+  if (need < 0) return (int)need;
+  if (scratch_bytes < need) return tfmpc_set_error(TFMPC_E_WORKSPACE, "tfmpc_ilqr_solve_host_async: scratch too small (%lld < %lld)", (long long)scratch_bytes, (long long)need);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t n = e->n, m = e->m;
+  const int64_t b_x0 = al(B * n * sizeof(real)), b_u = al(B * T * m * sizeof(real)), b_s = al(B * (T + 1) * n * sizeof(real));
+  const int64_t b_c = al(B * (T + 1) * sizeof(real)), b_st = al(B * 4 * sizeof(int32_t));
+  char *p = (char *)scratch;
+  real *d_x0 = (real *)p; p += b_x0;
+  real *d_ui = (real *)p; p += b_u;
+  real *d_a = (real *)p; p += b_u;
+  real *d_s = (real *)p; p += b_s;
+  real *d_c = (real *)p; p += b_c;
+  int32_t *d_st = (int32_t *)p; p += b_st;
+  void *d_ws = p;
+  const int64_t b_ws = scratch_bytes - (p - (char *)scratch);
+  CUDA_TRY(cudaMemcpyAsync(d_x0, x0, B * n * sizeof(real), cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaMemcpyAsync(d_ui, u_init, B * T * m * sizeof(real), cudaMemcpyHostToDevice, s));
+  int rc = tfmpc_ilqr_solve(e, B, T, d_x0, d_ui, opts, d_s, d_a, d_c, d_st, d_ws, b_ws, stream);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemcpyAsync(states, d_s, B * (T + 1) * n * sizeof(real), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(actions, d_a, B * T * m * sizeof(real), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(costs, d_c, B * (T + 1) * sizeof(real), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(stats, d_st, B * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  return TFMPC_OK;
+}
+
 // ------------------------------------------------------------------ LQR
 int tfmpc_lqr_solve(int64_t B, int n, int m, int T, const real *F, int64_t sF, const real *f, int64_t sf, const real *C, int64_t sC, const real *c,
                     int64_t sc, const real *x0, int terminal_zero, real *states, real *actions, real *costs, real *K, real *k, real *V, real *v,

@@ -327,3 +327,25 @@ def ilqr_solve_host(env, x0, u_init, opts=None, out=None):
     N.check(lib, lib.tfmpc_ilqr_solve_host(env.handle, C.c_int64(B), T, ins[0].p, ins[1].p, C.byref(opts), *[p.p for p in outs],
                                            N.stream_ptr()))
     return out
+
+
+def ilqr_host_scratch(env, B, T, device=None):
+    """Device scratch for one in-flight ilqr_solve_host_async call."""
+    env.lib.tfmpc_ilqr_solve_host_scratch_bytes.restype = C.c_int64
+    nbytes = env.lib.tfmpc_ilqr_solve_host_scratch_bytes(env.handle, C.c_int64(B), int(T))
+    if nbytes < 0:
+        N.check(env.lib, int(nbytes))
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device or torch.device("cuda", torch.cuda.current_device()))
+
+
+def ilqr_solve_host_async(env, x0, u_init, out, scratch, opts=None):
+    """tfmpc_ilqr_solve_host_async: HOST tensors in (x0 [B,n], u_init [B,T,m]) and out (dict as returned by ilqr_solve_host);
+    copies and solve are enqueued on the current stream, nothing is synchronised.  Use pinned tensors."""
+    B, T = u_init.shape[0], u_init.shape[1]
+    lib = env.lib
+    opts = opts or make_opts()
+    ins = [N.host_ptr(lib, t) for t in (x0, u_init)]
+    outs = [N.host_ptr(lib, t) for t in (out["states"], out["actions"], out["costs"])] + [N.host_ptr(lib, out["stats"], True)]
+    N.check(lib, lib.tfmpc_ilqr_solve_host_async(env.handle, C.c_int64(B), T, ins[0].p, ins[1].p, C.byref(opts), *[p.p for p in outs],
+                                                 C.c_void_p(scratch.data_ptr()), C.c_int64(scratch.numel()), N.stream_ptr()))
+    return out

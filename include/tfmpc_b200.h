@@ -215,10 +215,18 @@ int tfmpc_ilqr_solve(const tfmpc_env_t *env, int64_t B, int T, const tfmpc_real 
  *                        2 = closed form (default of the fp32 build), 0 = the reference's projected-Newton iteration
  *                        (optimization.py:6-101; default of the fp64 verification build)                        TFMPC_QP=closed|newton
  *   "queue_warps_per_sm" resident warps per SM of the queue kernel (default 18)                                  TFMPC_QUEUE_WPS
+ *   "queue_mode"         scheduling policy of the queue kernel: 1 = throughput (several batches in flight: the last
+ *                        problems of a batch stay in full warps, one per SM), 2 = latency (a batch that has the GPU to
+ *                        itself: the last problems spread over every warp slot and, once there are fewer problems than
+ *                        slots, each gets a whole warp -- the solo engine), 0 = auto (default): latency when no other
+ *                        stream of the device has a queue solve in flight at launch time                         TFMPC_QUEUE_MODE
  *   "queue_w_target"     warps the queue plans its pop size for: a warp pops clamp(ceil(unfinished / w_target), 1, 32)
- *                        problems (0 = one warp per SM: full warps until < 32 problems per SM are left; larger values
- *                        spread the last problems over more, emptier warps: lower single-batch latency, lower throughput
- *                        with several batches in flight)                                                         TFMPC_QUEUE_WTARGET
+ *                        problems (0 = the mode decides: one warp per SM / 12 warps per SM)                      TFMPC_QUEUE_WTARGET
+ *   "queue_solo_max"     a warp that popped <= this many problems runs them one after another on the solo engine (all
+ *                        lanes on one problem, everything in shared memory; a lone problem stays until it has converged);
+ *                        0 = never, 255 = the mode decides (0 / 1)                                               TFMPC_QUEUE_SOLO
+ *   "queue_w_solo"       once <= this many problems are unfinished every warp pops one (0 = the mode decides: the pop-size
+ *                        target / the number of warp slots)                                                      TFMPC_QUEUE_WSOLO
  *   "queue_patience"     idle polls before a warp takes fewer problems than planned (default 0)                 TFMPC_QUEUE_PATIENCE
  *   "queue_trace"        1 = record one scheduling-trace record per warp iteration (diagnostics)                 TFMPC_QUEUE_TRACE */
 int tfmpc_set_option(const char *name, int value);
@@ -227,8 +235,8 @@ int tfmpc_set_option(const char *name, int value);
  * out[3] = store passes (problems), out[4] = watchdog flag.  Synchronises the stream. */
 int tfmpc_ilqr_queue_counters(const void *workspace, int32_t *out, void *stream);
 /* Diagnostics: the scheduling trace of the last solve of (env, B, T) in `workspace` (option "queue_trace" on): records of
- * 4 uint32 = {acquire start (low 32 bits of the ns timer), ns waiting for tickets, ns working, lanes | rounds << 8 |
- * warp slot << 16}.  Returns the number of records copied to `out` (HOST memory), or a negative error.  Synchronises. */
+ * 8 uint32 = {acquire start (low 32 bits of the ns timer), ns waiting for tickets, ns working, lanes | rounds << 8 |
+ * warp slot << 16, ns state set-up, ns backward, ns search rounds, ns store pass}.  Returns the number of records copied to `out` (HOST memory), or a negative error.  Synchronises. */
 int64_t tfmpc_ilqr_queue_trace(const tfmpc_env_t *env, int64_t B, int T, const void *workspace, uint32_t *out, int64_t max_records,
                                void *stream);
 

@@ -1,6 +1,6 @@
 """GPU box helper: scheduling traces of the queue solver (option queue_trace): one lone C3 batch, then S streams x R batches
 in flight.  Writes gpurun_out/<tag>_trace.npz with, per solve, records [acquire start ns (32-bit), wait ns, work ns, lanes,
-rounds, warp slot]."""
+rounds, warp slot, set-up ns, backward ns, search ns, store-pass ns]."""
 import argparse, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -26,7 +26,7 @@ ops.set_option("queue_trace", 1)
 
 
 def unpack(t):
-    return np.stack([t[:, 0], t[:, 1], t[:, 2], t[:, 3] & 0xff, (t[:, 3] >> 8) & 0xff, t[:, 3] >> 16], axis=1)
+    return np.stack([t[:, 0], t[:, 1], t[:, 2], t[:, 3] & 0xff, (t[:, 3] >> 8) & 0xff, t[:, 3] >> 16, t[:, 4], t[:, 5], t[:, 6], t[:, 7]], axis=1)
 
 
 out = ops.ilqr_solve(nat, x0, u0, opts)

@@ -49,7 +49,7 @@ res = {"ms_per_batch": np.array(e0.elapsed_time(e1) / (S * R))}
 for i in range(S):
     for r in range(R):
         t = ops.queue_trace(nat, B, T, works[i][r])
-        res[f"s{i}_r{r}"] = np.stack([t[:, 0], t[:, 1], t[:, 2], t[:, 3] & 0xff, (t[:, 3] >> 8) & 0xff, t[:, 3] >> 16], axis=1)
+        res[f"s{i}_r{r}"] = np.stack([t[:, 0], t[:, 1], t[:, 2], t[:, 3] & 0xff, (t[:, 3] >> 8) & 0xff, t[:, 3] >> 16, t[:, 4], t[:, 5], t[:, 6], t[:, 7]], axis=1)
 os.makedirs("gpurun_out", exist_ok=True)
 np.savez_compressed(f"gpurun_out/{a.tag}_traceall.npz", **res)
 print(a.tag, "pipelined ms/batch", float(res["ms_per_batch"]))

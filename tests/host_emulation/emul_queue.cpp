@@ -31,7 +31,7 @@ static void fill_env(EnvSmall &s, int kind, int n, int nz, const double *p) {
 
 template <int KIND, int N, int M, int QP>
 static int run(const EnvSmall &e, const IlqrOpts &o, int B, int T, const real *x0, const real *u_init, real *states, real *actions,
-               real *costs, int32_t *stats, int nwarps, int w_target, int patience, int *ctrl_out) {
+               real *costs, int32_t *stats, int nwarps, int w_target, int patience, int solo_max, int *ctrl_out) {
   using namespace tq;
   constexpr int CHn = VecTraj<N, M>::CH;
   const int NH = ((T + 1) * CHn + CPH - 1) / CPH, row_r4 = NH * CPH;
@@ -46,7 +46,7 @@ static int run(const EnvSmall &e, const IlqrOpts &o, int B, int T, const real *x
   ctrl[C_TAIL] = B; ctrl[C_COUNT] = B; ctrl[C_ALIVE] = nwarps;
   QParams q;
   q.ctrl = ctrl.data(); q.ring = ring.data(); q.ring_mask = cap - 1; q.prob = prob.data(); q.traj = traj.data(); q.gain = gain.data();
-  q.B = B; q.T = T; q.row_r4 = row_r4; q.w_target = w_target; q.patience = patience; q.watchdog_ns = 120ull * 1000000000ull;
+  q.B = B; q.T = T; q.row_r4 = row_r4; q.w_target = w_target; q.patience = patience; q.solo_max = solo_max; q.w_solo = solo_max > 0 ? w_target : 0; q.watchdog_ns = 120ull * 1000000000ull;
   q.trace = nullptr; q.trace_cap = 0;
   q.x0 = x0; q.u_init = u_init; q.states = states; q.actions = actions; q.costs = costs; q.stats = stats;
   std::vector<WarpShared> shared(nwarps);
@@ -67,14 +67,14 @@ static int run(const EnvSmall &e, const IlqrOpts &o, int B, int T, const real *x
 
 extern "C" int emul_queue_solve(int kind, int n, int nz, const double *params, double atol, int max_iterations, double mu_min, double delta_0,
                                 double c1, const double *alphas, int B, int T, const real *x0, const real *u_init, real *states,
-                                real *actions, real *costs, int32_t *stats, int qp_mode, int nwarps, int w_target, int patience, int *ctrl_out) {
+                                real *actions, real *costs, int32_t *stats, int qp_mode, int nwarps, int w_target, int patience, int solo_max, int *ctrl_out) {
   EnvSmall e;
   fill_env(e, kind, n, nz, params);
   IlqrOpts o;
   o.atol = (real)atol; o.c1 = (real)c1; o.max_iterations = max_iterations; o.mu_min = mu_min; o.delta_0 = delta_0;
   for (int i = 0; i < N_ALPHA; i++) o.alphas[i] = (real)alphas[i];
   const bool closed = qp_mode == QP_CLOSED;
-#define RUN(K, NN, QP) return run<K, NN, NN, QP>(e, o, B, T, x0, u_init, states, actions, costs, stats, nwarps, w_target, patience, ctrl_out)
+#define RUN(K, NN, QP) return run<K, NN, NN, QP>(e, o, B, T, x0, u_init, states, actions, costs, stats, nwarps, w_target, patience, solo_max, ctrl_out)
   if (kind == TFMPC_ENV_NAVIGATION && n == 2 && nz <= 2) { if (closed) RUN(TFMPC_ENV_NAVIGATION_Z2, 2, QP_CLOSED); else RUN(TFMPC_ENV_NAVIGATION_Z2, 2, QP_NEWTON); }   // same dispatch as ilqr_queue.cu
   if (kind == TFMPC_ENV_NAVIGATION && n == 2) { if (closed) RUN(TFMPC_ENV_NAVIGATION, 2, QP_CLOSED); else RUN(TFMPC_ENV_NAVIGATION, 2, QP_NEWTON); }
   if (kind == TFMPC_ENV_NAVLQR && n == 1) { if (closed) RUN(TFMPC_ENV_NAVLQR, 1, QP_CLOSED); else RUN(TFMPC_ENV_NAVLQR, 1, QP_NEWTON); }

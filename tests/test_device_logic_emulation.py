@@ -112,11 +112,11 @@ def emul2():
         assert rc == 0
         return bufs
 
-    def queue(prec, cfg, x0, u_init, qp, nwarps, w_target, patience=4):
+    def queue(prec, cfg, x0, u_init, qp, nwarps, w_target, patience=4, solo_max=4):
         kind, n, nz, params, x0, u, B, T, bufs = prep(prec, cfg, x0, u_init)
         ctrl = np.zeros(libs[prec].emul_queue_ctrl_ints(), np.int32)
         rc = libs[prec].emul_queue_solve(kind, n, nz, p(params), C.c_double(5e-3), 100, C.c_double(1e-6), C.c_double(2.0), C.c_double(0.0),
-                                        p(ALPHAS), B, T, p(x0), p(u), *[p(b) for b in bufs], qp, nwarps, w_target, patience, p(ctrl))
+                                        p(ALPHAS), B, T, p(x0), p(u), *[p(b) for b in bufs], qp, nwarps, w_target, patience, solo_max, p(ctrl))
         assert rc == 0, f"queue solver flagged {rc}"
         return bufs, ctrl
     return seq, queue
@@ -155,15 +155,16 @@ def test_closed_form_qp_agreement_with_oracle(emul2, prec):
 
 @pytest.mark.parametrize("prec", ["f32", "f64"])
 @pytest.mark.parametrize("qp", [0, 2])
-@pytest.mark.parametrize("B,T,nwarps,w_target", [(70, 50, 3, 2), (40, 50, 2, 4), (33, 1, 2, 1), (37, 7, 2, 1), (20, 9, 1, 1)])
-def test_queue_solver_equals_sequential_solve(emul2, prec, qp, B, T, nwarps, w_target):
+@pytest.mark.parametrize("B,T,nwarps,w_target,solo_max", [(70, 50, 3, 2, 4), (40, 50, 2, 4, 4), (33, 1, 2, 1, 4), (37, 7, 2, 1, 4), (20, 9, 1, 1, 4),
+                                                          (70, 50, 3, 2, 0), (20, 9, 1, 1, 0), (24, 50, 6, 24, 4), (30, 50, 3, 4, 1)])
+def test_queue_solver_equals_sequential_solve(emul2, prec, qp, B, T, nwarps, w_target, solo_max):
     """The persistent work-queue kernel body (queue_core.cuh), executed warp by warp on the CPU, must reproduce the sequential
     per-problem composition solve_one() BIT FOR BIT: same arithmetic, different schedule (ticket queue, line-search rounds with
     lanes shared between problems, store pass, cooperative line staging, partially filled warps, horizons shorter than a line)."""
     seq, queue = emul2
     cfg, x0, u0 = _nav_batch(B, T, 3 + B)
     ref = seq(prec, cfg, x0, u0, qp)
-    got, ctrl = queue(prec, cfg, x0, u0, qp, nwarps, w_target)
+    got, ctrl = queue(prec, cfg, x0, u0, qp, nwarps, w_target, solo_max=solo_max)
     for name, a, b in zip(("states", "actions", "costs", "stats"), ref, got):
         assert np.array_equal(a, b), name
     assert ctrl[64] == B and ctrl[0] == ctrl[32]             # every problem finished, every ticket consumed

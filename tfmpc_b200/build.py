@@ -63,7 +63,9 @@ def build(force=False, verbose=False, precisions=("f32", "f64")):
         outputs[prec] = out
         if not force and os.path.exists(out) and os.path.getmtime(out) >= newest:
             continue
-        extra = ["-DTFMPC_F64"] if prec == "f64" else ([f for f in os.environ.get("TFMPC_F32_FLAGS", F32_FLAGS).split() if f])
+        # fp64 verification build: no FMA contraction, so that two code shapes of the same expressions (thread-per-problem,
+        # warp-cooperative, tick kernels) and the gcc-built oracle round identically
+        extra = ["-DTFMPC_F64", "-fmad=false"] if prec == "f64" else ([f for f in os.environ.get("TFMPC_F32_FLAGS", F32_FLAGS).split() if f])
         for s in SOURCES:
             jobs.append((os.path.join(CSRC, s), os.path.join(OBJ, f"{os.path.splitext(s)[0]}_{prec}.o"), extra, verbose))
     if jobs:

@@ -4,6 +4,7 @@
 #include <atomic>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 #include "queue_core.cuh"
 
@@ -38,10 +39,56 @@ int env_int(const char *name, int dflt) {
 }
 
 std::atomic<int> g_wps{env_int("TFMPC_QUEUE_WPS", kMaxWarpsPerSM)};
-std::atomic<int> g_w_target{env_int("TFMPC_QUEUE_WTARGET", 0)};   // 0 = one warp per SM
+// Scheduling policy.  The same kernel serves two regimes that want opposite things from the last few thousand problems of a
+// batch: with several batches in flight (pipelined throughput) the stragglers should occupy as few warps as possible --
+// full warps, one per SM, lane-per-problem -- because every other warp slot is doing another batch's bulk work; a batch
+// that has the GPU to itself (latency) should spread them over all warp slots and, once there are fewer problems than
+// slots, give each problem a whole warp (the solo engine: ~34 us per iteration against ~75 us on one lane).
+//   mode 1 = throughput: pop-size target = one warp per SM, solo engine off
+//   mode 2 = latency:    pop-size target = 12 warps per SM, solo once unfinished <= warp slots
+//   mode 0 = auto:       latency when no other stream of this device has a queue solve in flight at launch time
+// Each of the knobs below overrides the mode's choice when set (> 0; solo_max: anything but 255).
+std::atomic<int> g_mode{env_int("TFMPC_QUEUE_MODE", 0)};
+std::atomic<int> g_w_target{env_int("TFMPC_QUEUE_WTARGET", 0)};
+std::atomic<int> g_w_solo{env_int("TFMPC_QUEUE_WSOLO", 0)};
+std::atomic<int> g_solo_max{env_int("TFMPC_QUEUE_SOLO", 255)};   // 255 = the mode decides
 std::atomic<int> g_patience{env_int("TFMPC_QUEUE_PATIENCE", 0)};
 std::atomic<int> g_trace{env_int("TFMPC_QUEUE_TRACE", 0)};
-constexpr int kTraceCap = 1 << 18;   // warp iterations recorded when the trace is on (4 MB)
+std::atomic<int> g_last_mode{0};   // what the last launch chose (diagnostics)
+
+// queue solves launched and not yet known to be complete: (stream, event recorded behind the solve kernel)
+struct InFlight { cudaStream_t stream; cudaEvent_t ev; int device; bool active; };
+constexpr int kInFlightSlots = 64;
+InFlight g_inflight[kInFlightSlots];
+std::mutex g_inflight_mu;
+
+// true when another stream of `device` has a queue solve in flight (or when that cannot be determined)
+bool others_in_flight(int device, cudaStream_t s) {
+  bool busy = false;
+  for (auto &f : g_inflight) {
+    if (!f.active || f.device != device) continue;
+    if (cudaEventQuery(f.ev) == cudaSuccess) { f.active = false; continue; }
+    cudaGetLastError();   // cudaErrorNotReady is not an error
+    if (f.stream != s) busy = true;
+  }
+  return busy;
+}
+void note_in_flight(int device, cudaStream_t s) {
+  InFlight *slot = nullptr;
+  for (auto &f : g_inflight)
+    if (f.active && f.device == device && f.stream == s) { slot = &f; break; }   // a later solve on the same stream supersedes the earlier one
+  if (!slot)
+    for (auto &f : g_inflight)
+      if (!f.active && (!f.ev || f.device == device)) { slot = &f; break; }
+  if (!slot) return;   // table full: the next launch then simply sees fewer solves than there are
+  if (!slot->ev) {
+    if (cudaEventCreateWithFlags(&slot->ev, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); slot->ev = nullptr; return; }
+  }
+  slot->device = device; slot->stream = s;
+  slot->active = cudaEventRecord(slot->ev, s) == cudaSuccess;
+  if (!slot->active) cudaGetLastError();
+}
+constexpr int kTraceCap = 1 << 18;   // warp iterations recorded when the trace is on (8 words each: 8 MB)
 
 int device_sms(int device) {
   static int cached[64] = {0};
@@ -76,7 +123,7 @@ Plan make_plan(const tfmpc_env *e, int64_t B, int T) {
   p.o_prob = off; off += al(B * (int64_t)sizeof(tq::QProb));
   p.o_traj = off; off += al(2 * B * p.row_r4 * (int64_t)sizeof(R4));
   p.o_gain = off; off += al((int64_t)p.nwarps * T * p.ch2 * 32 * (int64_t)sizeof(tq::R2));
-  p.o_trace = off; off += al((int64_t)kTraceCap * 16);
+  p.o_trace = off; off += al((int64_t)kTraceCap * 32);
   p.bytes = off;
   return p;
 }
@@ -94,9 +141,20 @@ int launch(const tfmpc_env *e, int64_t B, int T, const real *x0, const real *u_i
   q.traj = (R4 *)(base + pl.o_traj);
   q.gain = (tq::R2 *)(base + pl.o_gain);
   q.B = (int)B; q.T = T; q.row_r4 = pl.row_r4;
-  const int wt = g_w_target.load();
-  q.w_target = wt > 0 ? wt : device_sms(e->device);
+  // scheduling policy of this launch (see g_mode above)
+  int mode = g_mode.load();
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  const bool capturing = cudaStreamIsCapturing(s, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone;
+  if (capturing) cudaGetLastError();
+  std::unique_lock<std::mutex> lock(g_inflight_mu, std::defer_lock);
+  if (!capturing) lock.lock();
+  if (mode != 1 && mode != 2) mode = (capturing || others_in_flight(e->device, s)) ? 1 : 2;
+  g_last_mode.store(mode);
+  const int sms = device_sms(e->device), wt = g_w_target.load(), ws_ = g_w_solo.load(), sm_ = g_solo_max.load();
+  q.w_target = wt > 0 ? wt : (mode == 2 ? 12 * sms : sms);
   q.patience = std::max(0, g_patience.load());
+  q.solo_max = std::max(0, std::min(32, sm_ != 255 ? sm_ : (mode == 2 ? 1 : 0)));
+  q.w_solo = q.solo_max > 0 ? (ws_ > 0 ? ws_ : (mode == 2 ? pl.nwarps : q.w_target)) : 0;
   q.watchdog_ns = 4000000000ull;   // 4 s without progress for one warp: give up (status TFMPC_ST_ABORTED) instead of hanging the device
   q.x0 = x0; q.u_init = u_init; q.states = states; q.actions = actions; q.costs = costs; q.stats = stats;
   q.trace = g_trace.load() ? (unsigned *)(base + pl.o_trace) : nullptr;
@@ -108,6 +166,7 @@ int launch(const tfmpc_env *e, int64_t B, int T, const real *x0, const real *u_i
   if (can_close && qp == QP_CLOSED) k_queue_solve<KIND, N, M, (M <= 2 ? QP_CLOSED : QP_NEWTON)><<<pl.nwarps, 32, 0, s>>>(e->es, o, q);
   else k_queue_solve<KIND, N, M, QP_NEWTON><<<pl.nwarps, 32, 0, s>>>(e->es, o, q);
   LAUNCH_CHECK();
+  if (!capturing) note_in_flight(e->device, s);
   return TFMPC_OK;
 }
 
@@ -124,6 +183,10 @@ int queue_ilqr_option(const char *name, int value, int *previous) {
   else if (!strcmp(name, "queue_w_target")) t = &g_w_target;
   else if (!strcmp(name, "queue_patience")) t = &g_patience;
   else if (!strcmp(name, "queue_trace")) t = &g_trace;
+  else if (!strcmp(name, "queue_solo_max")) t = &g_solo_max;
+  else if (!strcmp(name, "queue_w_solo")) t = &g_w_solo;
+  else if (!strcmp(name, "queue_mode")) t = &g_mode;
+  else if (!strcmp(name, "queue_last_mode")) { *previous = g_last_mode.load(); return 1; }
   if (!t) return 0;
   *previous = t->exchange(value);
   return 1;
@@ -136,14 +199,14 @@ int queue_ilqr_counters(const void *ws, int *out, int n, cudaStream_t s) {
   return TFMPC_OK;
 }
 
-// scheduling trace of the last solve in this workspace (option "queue_trace" must have been on): up to max_records records of 4 uint32
+// scheduling trace of the last solve in this workspace (option "queue_trace" must have been on): up to max_records records of 8 uint32
 int64_t queue_ilqr_trace(const tfmpc_env *e, int64_t B, int T, const void *ws, unsigned *out, int64_t max_records, cudaStream_t s) {
   const Plan pl = make_plan(e, std::min(B, kMaxSlice), T);
   int n = 0;
   CUDA_TRY(cudaMemcpyAsync(&n, (const char *)ws + pl.o_ctrl + 4 * tq::C_TRACE, 4, cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaStreamSynchronize(s));
   int64_t cnt = std::min<int64_t>(std::min<int64_t>(n, kTraceCap), max_records);
-  if (cnt > 0) CUDA_TRY(cudaMemcpyAsync(out, (const char *)ws + pl.o_trace, cnt * 16, cudaMemcpyDeviceToHost, s));
+  if (cnt > 0) CUDA_TRY(cudaMemcpyAsync(out, (const char *)ws + pl.o_trace, cnt * 32, cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaStreamSynchronize(s));
   return cnt;
 }

@@ -19,6 +19,16 @@
 // the queue empty retire (freeing their SM slots for the next batch's kernel), and near the end the pop size shrinks so
 // that the last stragglers each own a warp (all 11 step sizes in one round).
 //
+// The solo engine.  When few problems are left a warp pops only a handful, and a lane-per-problem iteration then costs the
+// full serial latency of one thread (~85 us for C3: 40 us backward, 2 x 20 us rollouts) with 31 lanes idle.  A warp that
+// popped <= solo_max problems instead runs them one after another with ALL lanes working on one problem, everything in
+// shared memory: the linearisation of the whole horizon is computed first, one timestep per lane; the Riccati sweep then
+// assembles each timestep's Q block with one matrix entry per lane (same expressions, same summation order as the
+// one-thread code, so the results are bit-identical), hands it over through shared memory, and every lane runs the
+// controller and the value update redundantly (no divergence, no second hand-over); the 11 step sizes roll out on 11
+// lanes at once and keep their candidates in shared memory, so the accepted one is copied, not replayed.  A warp that
+// popped a single problem keeps it until it has converged (no queue round trip, no global trajectory traffic at all).
+//
 // Memory traffic.  Trajectories are PROBLEM-major (one problem = one contiguous, 64-byte aligned row) and move between
 // HBM/L2 and shared memory only as 64-byte half-lines (4 steps for n = m = 2): 4 lanes fetch one half-line with cp.async
 // (8 rows per instruction instead of 32 scattered sectors), the store pass overwrites the staged nominal records in place
@@ -51,12 +61,15 @@ struct QParams {
   int B, T, row_r4;
   int w_target;                 // warps the pop size is planned for: pop = clamp(ceil(outstanding / w_target), 1, 32)
   int patience;                 // idle polls before a warp settles for fewer problems than the planned pop size
+  int solo_max;                 // a warp that popped <= solo_max problems runs them one after another on the solo engine (0 = never)
+  int w_solo;                   // once <= w_solo problems are unfinished every warp pops ONE (and keeps it on the solo engine)
   unsigned long long watchdog_ns;
   const real *x0, *u_init;
   real *states, *actions, *costs;
   int32_t *stats;
-  // optional scheduling trace (diagnostics, option "queue_trace"): one record per warp iteration
-  //   {acquire start [ns, low 32 bits of %globaltimer], wait for tickets [ns], work [ns], lanes | rounds << 8 | warp slot << 16}
+  // optional scheduling trace (diagnostics, option "queue_trace"): one record of 8 words per warp iteration
+  //   {acquire start [ns, low 32 bits of %globaltimer], wait for tickets [ns], work [ns], lanes | rounds << 8 | warp slot << 16,
+  //    state set-up [ns], backward [ns], search rounds [ns], store pass [ns]}   (the rest of `work` is results / re-queue)
   unsigned *trace;
   int trace_cap;
 };
@@ -327,6 +340,321 @@ WD void rollout_round(WarpRT &rt, WarpSmem &sm, const EnvSmall &e, int T, int NH
   rt.template cp_wait<0>();
 }
 
+// ================================================================== the solo engine (see the header comment)
+template <int N, int M>
+struct Solo {
+  static constexpr int Z = N + M, CHn = VecTraj<N, M>::CH;
+#ifdef TFMPC_QUEUE_NO_SOLO
+  static constexpr bool supported = false;                // A/B builds
+#else
+  static constexpr bool supported = Z * Z <= 32;          // one Q entry per lane
+#endif
+  static constexpr int LIN = N * Z + Z + Z * Z + 1;        // reals per linearised timestep: F = [f_x f_u] [N][Z], l_z [Z], l_zz [Z][Z], l
+  static constexpr int G = M * N + M;                      // reals per timestep of gains: K [M][N], k [M]
+  static constexpr int QBS = (QB<N, M>::SIZE + 3) / 4 * 4;
+  struct Map { int nom, xq, gain, lin, cand, bytes; };     // byte offsets inside the warp's shared memory
+  HD static Map map(int T, int row_r4) {
+    Map m;
+    int o = 0;
+    m.nom = o; o += row_r4 * (int)sizeof(R4);
+    m.xq = o; o += 2 * QBS * (int)sizeof(real);
+    m.gain = o; o += (T * G * (int)sizeof(real) + 15) / 16 * 16;
+    m.lin = m.cand = o;                                     // the linearisation is dead once the backward sweep is over
+    const int lin_b = T * LIN * (int)sizeof(real), cand_b = N_ALPHA * row_r4 * (int)sizeof(R4);
+    o += lin_b > cand_b ? lin_b : cand_b;
+    m.bytes = o;
+    return m;
+  }
+};
+
+// derivatives (ilqr.py:84-92) of the whole nominal trajectory, one timestep per lane, into shared memory
+template <int KIND, int N, int M>
+WD void solo_linearize(WarpRT &rt, char *smb, const typename Solo<N, M>::Map &mp, const EnvSmall &e, int T) {
+  typedef Solo<N, M> S;
+  constexpr int Z = S::Z;
+  const VecTraj<N, M> nom = {(R4 *)(smb + mp.nom), S::CHn, 1};
+  real *lin = (real *)(smb + mp.lin);
+  for (int t = rt.lane; t < T; t += 32) {
+    real x[N], u[M];
+    nom.load_xu(t, x, u);
+    Lin<N, M> L;
+    env_linearize<KIND, N, M>(e, x, u, L);
+    real *r = lin + t * S::LIN;
+#pragma unroll
+    for (int p = 0; p < N; p++) {
+#pragma unroll
+      for (int c = 0; c < N; c++) r[p * Z + c] = L.f_x[p * N + c];
+#pragma unroll
+      for (int c = 0; c < M; c++) r[p * Z + N + c] = L.f_u[p * M + c];
+    }
+#pragma unroll
+    for (int i = 0; i < N; i++) r[N * Z + i] = L.l_x[i];
+#pragma unroll
+    for (int i = 0; i < M; i++) r[N * Z + N + i] = L.l_u[i];
+    real *zz = r + N * Z + Z;
+#pragma unroll
+    for (int a = 0; a < Z; a++)
+#pragma unroll
+      for (int b = 0; b < Z; b++)
+        zz[a * Z + b] = (a < N && b < N) ? L.l_xx[(a < N ? a : 0) * N + (b < N ? b : 0)]
+                        : (a < N) ? L.l_xu[(a < N ? a : 0) * M + (b >= N ? b - N : 0)]
+                        : (b < N) ? L.l_xu[(b < N ? b : 0) * M + (a >= N ? a - N : 0)]     // l_ux = l_xu^T (ilqr.py:131)
+                                  : L.l_uu[(a >= N ? a - N : 0) * M + (b >= N ? b - N : 0)];
+    r[S::LIN - 1] = L.l;
+  }
+  rt.syncwarp();
+}
+
+// iLQR.backward (ilqr.py:94-172) of ONE problem by the whole warp.  Stage 1 of every timestep (assemble_q) is spread over
+// the lanes -- lane a * Z + b computes entry (a, b) of [Q_xx Q_xu; Q_ux Q_uu] and its regularised twin, the lanes with
+// b == 0 also Q_z[a] -- with exactly the expressions of assemble_q (the structural zeros it skips add +0 here); stages
+// 2 and 3 run redundantly on every lane.  Gains go to shared memory.  Returns backward_pass()'s status.
+template <int KIND, int N, int M, int QP>
+WD int solo_backward(WarpRT &rt, char *smb, const typename Solo<N, M>::Map &mp, const EnvSmall &e, int T, real mu, real &J, real &dV1,
+                     real &dV2, real &gsum) {
+  typedef Solo<N, M> S;
+  typedef QB<N, M> Q;
+  constexpr int Z = S::Z;
+  const VecTraj<N, M> nom = {(R4 *)(smb + mp.nom), S::CHn, 1};
+  const real *lin = (const real *)(smb + mp.lin);
+  real *xq = (real *)(smb + mp.xq), *gain = (real *)(smb + mp.gain);
+  const int lane = rt.lane;
+  const bool worker = lane < Z * Z;
+  const int a = worker ? lane / Z : 0, b = worker ? lane % Z : 0;
+  int off_q = -1, off_qr = -1, off_z = -1;
+  if (worker) {
+    if (a < N && b < N) off_q = Q::OXX + a * N + b;
+    else if (a >= N && b < N) { off_q = Q::OUX + (a - N) * N + b; off_qr = Q::OUXR + (a - N) * N + b; }
+    else if (a >= N && b >= N) { off_q = Q::OUU + (a - N) * M + (b - N); off_qr = Q::OUUR + (a - N) * M + (b - N); }
+    if (b == 0) off_z = a < N ? Q::OX + a : Q::OU + (a - N);
+  }
+  real V_x[N], V_xx[N * N], x[N], u[M];
+  nom.load_x(T, x);
+  env_final_quad<KIND, N, M>(e, x, J, V_x, V_xx);  // :101-104
+  dV1 = 0; dV2 = 0; gsum = 0;
+  int status = 0;
+  // this lane's slice of the linearised timestep, loaded one step ahead (the loads do not depend on the value function)
+  real Fa[N], Fb[N], lzz, lz, lt, Fa_n[N], Fb_n[N], lzz_n, lz_n, lt_n;
+  {
+    const real *r = lin + (T - 1) * S::LIN;
+#pragma unroll
+    for (int p = 0; p < N; p++) { Fa_n[p] = r[p * Z + a]; Fb_n[p] = r[p * Z + b]; }
+    lzz_n = r[N * Z + Z + a * Z + b]; lz_n = r[N * Z + a]; lt_n = r[S::LIN - 1];
+  }
+  for (int t = T - 1; t >= 0; t--) {
+#pragma unroll
+    for (int p = 0; p < N; p++) { Fa[p] = Fa_n[p]; Fb[p] = Fb_n[p]; }
+    lzz = lzz_n; lz = lz_n; lt = lt_n;
+    real qz, qe, qr;
+    {
+      real s = 0;
+#pragma unroll
+      for (int p = 0; p < N; p++) s += Fa[p] * V_x[p];
+      qz = lz + s;
+      real sq = 0, sqr = 0;
+#pragma unroll
+      for (int p = 0; p < N; p++) {
+        real tp = 0, tr = 0;
+#pragma unroll
+        for (int c = 0; c < N; c++) {
+          tp += Fa[c] * V_xx[c * N + p];
+          tr += Fa[c] * (c == p ? V_xx[c * N + p] + mu * (real)1 : V_xx[c * N + p]);
+        }
+        sq += tp * Fb[p];
+        sqr += tr * Fb[p];
+      }
+      qe = lzz + sq; qr = lzz + sqr;
+    }
+    real *X = xq + (t & 1) * S::QBS;   // two hand-over blocks: the reads of step t + 2 are ordered before these writes by step t + 1's barrier
+    if (off_q >= 0) X[off_q] = qe;
+    if (off_qr >= 0) X[off_qr] = qr;
+    if (off_z >= 0) X[off_z] = qz;
+    rt.syncwarp();
+    Q q;
+#pragma unroll
+    for (int i = 0; i < Q::SIZE; i++) q.v[i] = X[i];
+    nom.load_xu(t, x, u);
+    {
+      const real *r = lin + (t > 0 ? t - 1 : 0) * S::LIN;
+#pragma unroll
+      for (int p = 0; p < N; p++) { Fa_n[p] = r[p * Z + a]; Fb_n[p] = r[p * Z + b]; }
+      lzz_n = r[N * Z + Z + a * Z + b]; lz_n = r[N * Z + a]; lt_n = r[S::LIN - 1];
+    }
+    real K[M * N], k[M];
+    const int st = controller<KIND, N, M, QP>(e, q, V_xx, u, K, k);
+    if (st == 1) { status = 1; break; }   // unconstrained Cholesky failed: the caller retries (ilqr.py:305-309)
+    if (st) status = st;
+    value_update<N, M>(q, K, k, lt, V_x, V_xx, J, dV1, dV2);   // (spread over the lanes it is no faster: the shuffles that
+                                                                            //  re-broadcast V sit on the critical path -- measured 23.8 vs 22.5 us)
+    real mx = 0;
+#pragma unroll
+    for (int i = 0; i < M; i++) {
+      real v = r_abs(k[i]) / (r_abs(u[i]) + (real)1.0);
+      mx = (i == 0 || v > mx) ? v : mx;
+    }
+    gsum += mx;
+    if (lane == 0) {
+      real *g = gain + t * S::G;
+#pragma unroll
+      for (int i = 0; i < M * N; i++) g[i] = K[i];
+#pragma unroll
+      for (int i = 0; i < M; i++) g[M * N + i] = k[i];
+    }
+  }
+  rt.syncwarp();
+  return status;
+}
+
+// the line search (_forward, ilqr.py:317-355): all N_ALPHA step sizes at once, one per lane, candidates kept in shared memory
+template <int KIND, int N, int M>
+WD void solo_search(WarpRT &rt, char *smb, const typename Solo<N, M>::Map &mp, const EnvSmall &e, const IlqrOpts &o, int T, int row_r4,
+                    const Prob &p, bool &accept, int &chosen, int &rollouts, real &residual) {
+  typedef Solo<N, M> S;
+  const VecTraj<N, M> nom = {(R4 *)(smb + mp.nom), S::CHn, 1};
+  const real *gain = (const real *)(smb + mp.gain);
+  const CostSink none = {nullptr, 0};
+  const bool run = rt.lane < N_ALPHA;
+  const real alpha = o.alphas[run ? rt.lane : 0];
+  real J = 0, res = 0;
+  if (run) {
+    const VecTraj<N, M> cand = {(R4 *)(smb + mp.cand) + rt.lane * row_r4, S::CHn, 1};
+    real x[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) x[i] = 0;
+#pragma unroll 2   // lets the loads of step t + 1 (independent of x) be scheduled above the arithmetic of step t
+    for (int t = 0; t < T; t++) {
+      NomRec<N, M> use;
+      const real *g = gain + t * S::G;
+#pragma unroll
+      for (int i = 0; i < M * N; i++) use.K[i] = g[i];
+#pragma unroll
+      for (int i = 0; i < M; i++) use.k[i] = g[M * N + i];
+      nom.load_xu(t, use.xh, use.uh);
+      if (t == 0) {
+#pragma unroll
+        for (int i = 0; i < N; i++) x[i] = use.xh[i];
+      }
+      forward_step<KIND, N, M>(e, alpha, use, t, x, cand, none, J, res);
+    }
+    cand.store_x(T, x);
+    J += env_final_cost<KIND, N, M>(e, x);
+  }
+  const unsigned acc = rt.ballot(run && ls_accepts(o, alpha, p.J_hat, p.dV1, p.dV2, J));   // first accept wins (:322-353)
+  accept = acc != 0;
+  chosen = accept ? nth_set_bit(acc, 0) : N_ALPHA - 1;   // all rejected: _forward returns the last candidate
+  rollouts = accept ? chosen + 1 : N_ALPHA;
+  residual = rt.shfl(res, chosen);
+}
+
+// Runs problem b on the solo engine: one iteration (sticky = false; the problem's state goes back to global memory for
+// the re-queue) or all of them (sticky = true).  Returns true when the problem has finished (results written).
+template <int KIND, int N, int M, int QP, class WarpSmem>
+WD bool solo_run(WarpRT &rt, WarpSmem &sm, const EnvSmall &e, const IlqrOpts &o, const QParams &q, int b, bool fresh, bool sticky,
+                 int &n_iter, int &n_taken, unsigned &ns_lin, unsigned &ns_bwd, unsigned &ns_search) {
+  typedef Solo<N, M> S;
+  const int lane = rt.lane, T = q.T, row_r4 = q.row_r4;
+  char *smb = (char *)&sm;
+  const typename S::Map mp = S::map(T, row_r4);
+  R4 *nom_s = (R4 *)(smb + mp.nom);
+  const VecTraj<N, M> nom = {nom_s, S::CHn, 1};
+  const CostSink none = {nullptr, 0};
+  Prob p;
+  prob_init(p);
+  rt.syncwarp();   // whatever the warp did in this shared memory before is over
+  if (fresh) {     // iLQR.start (ilqr.py:53-82) with the supplied initial actions
+    if (lane == 0) {
+      real xs[N];
+#pragma unroll
+      for (int i = 0; i < N; i++) xs[i] = q.x0[(int64_t)b * N + i];
+      start_pass<KIND, N, M>(e, T, xs, q.u_init + (int64_t)b * T * M, nom, none);
+    }
+  } else {
+    const QProb s = q.prob[b];
+    p.mu = s.mu; p.delta = s.delta; p.iteration = s.iteration; p.n_bwd = s.n_bwd; p.n_fwd = s.n_fwd;
+    p.cur = s.cg & 1; p.guard = s.cg >> 1;
+    const R4 *row = traj_row(q, p.cur, b);
+    for (int i = lane; i < row_r4; i += 32) nom_s[i] = row[i];
+  }
+  rt.syncwarp();
+  bool write_back = fresh;   // the global copy of the nominal is stale (or was never written)
+  for (;;) {
+    // ---- backward (+ the retry wrapper _backward, ilqr.py:285-315)
+    unsigned long long tq0 = 0, tq1 = 0, tq2 = 0;
+    if (q.trace) tq0 = rt.now_ns();
+    solo_linearize<KIND, N, M>(rt, smb, mp, e, T);
+    if (q.trace) tq1 = rt.now_ns();
+    {
+      double mu_l = p.mu, delta_l = p.delta;   // the retry bump is local (:308-309,315)
+      int tries = 0, bst;
+      real gsum;
+      for (;;) {
+        bst = solo_backward<KIND, N, M, QP>(rt, smb, mp, e, T, (real)mu_l, p.J_hat, p.dV1, p.dV2, gsum);
+        p.n_bwd++;
+        if (bst != 1 || ++tries > 200) break;
+        delta_l = fmax(o.delta_0, delta_l * o.delta_0);
+        mu_l = fmax(o.mu_min, mu_l * delta_l);
+      }
+      p.phase = PH_SEARCH;   // g_norm test, ilqr.py:243-248 (same rules as tick_backward)
+      const real g = gsum / (real)T;
+      if (bst) { p.status = TFMPC_ST_NONPD; p.phase = PH_DONE; }
+      else if (!(g == g)) { p.status = TFMPC_ST_NAN; p.phase = PH_DONE; }
+      else if (g < o.atol) { p.status = TFMPC_ST_CONVERGED; p.phase = PH_DONE; }
+    }
+    n_iter++;
+    if (q.trace) { tq2 = rt.now_ns(); ns_lin += (unsigned)(tq1 - tq0); ns_bwd += (unsigned)(tq2 - tq1); }
+    // ---- line search and schedule (ilqr.py:253-270)
+    if (p.phase == PH_SEARCH) {
+      bool accept;
+      int chosen, rollouts;
+      real residual;
+      solo_search<KIND, N, M>(rt, smb, mp, e, o, T, row_r4, p, accept, chosen, rollouts, residual);
+      if (tick_finish(o, accept, residual, rollouts, p)) {   // the candidate becomes the nominal
+        const R4 *cand = (const R4 *)(smb + mp.cand) + chosen * row_r4;
+        rt.syncwarp();
+        for (int i = lane; i < row_r4; i += 32) nom_s[i] = cand[i];
+        p.cur ^= 1;
+        write_back = true;
+        n_taken++;
+      }
+      rt.syncwarp();
+      if (q.trace) ns_search += (unsigned)(rt.now_ns() - tq2);
+    }
+    if (p.phase == PH_DONE) break;
+    if (!sticky) {   // one iteration per visit: state back to global memory, the caller re-queues the problem
+      if (write_back) {
+        R4 *row = traj_row(q, p.cur, b);
+        for (int i = lane; i < row_r4; i += 32) row[i] = nom_s[i];
+      }
+      if (lane == 0) {
+        QProb s;
+        s.mu = p.mu; s.delta = p.delta; s.iteration = p.iteration; s.n_bwd = p.n_bwd; s.n_fwd = p.n_fwd; s.cg = (p.cur & 1) | (p.guard << 1);
+        q.prob[b] = s;
+      }
+      return false;
+    }
+  }
+  // ---- finished: results in the reference layouts (states [B,T+1,n], actions [B,T,m], costs [B,T+1])
+  real *Sx = q.states + (int64_t)b * (T + 1) * N, *A = q.actions + (int64_t)b * T * M, *Cc = q.costs + (int64_t)b * (T + 1);
+  for (int t = lane; t <= T; t += 32) {
+    real x[N], u[M];
+    nom.load_xu(t, x, u);
+#pragma unroll
+    for (int i = 0; i < N; i++) Sx[t * N + i] = x[i];
+    if (t < T) {
+#pragma unroll
+      for (int i = 0; i < M; i++) A[t * M + i] = u[i];
+      Cc[t] = env_cost<KIND, N, M>(e, x, u);
+    } else {
+      Cc[T] = env_final_cost<KIND, N, M>(e, x);
+    }
+  }
+  if (lane == 0) {
+    int32_t *st = q.stats + (int64_t)b * 4;
+    st[0] = p.iteration; st[1] = p.n_bwd; st[2] = p.n_fwd; st[3] = p.status;
+  }
+  return true;
+}
+
 // ---- queue: lane 0 claims `take` consecutive tickets starting at h (0 = this warp retires).
 // C_COUNT is a semaphore of queued tickets: a claim is one atomic subtraction (over-draws are handed back), then one
 // atomic add on C_HEAD numbers the tickets.  No compare-and-swap loop: with ~2,400 warps popping every ~100 us an
@@ -343,6 +671,7 @@ WD int q_acquire(WarpRT &rt, const QParams &q, int &h_out) {
     if (P <= 0) return 0;
     int g = (P + q.w_target - 1) / q.w_target;
     g = g < 1 ? 1 : (g > 32 ? 32 : g);
+    if (P <= q.w_solo) g = 1;
     const int avail = rt.ld_relaxed(ctrl + C_COUNT);
     const bool settle = idle >= q.patience;   // waited long enough: take whatever is there
     if (avail >= g || (avail > 0 && settle)) {
@@ -382,6 +711,7 @@ WD void queue_warp_main(WarpRT &rt, const EnvSmall &e, const IlqrOpts &o, const 
   const CostSink none = {nullptr, 0};
   R2 *gain_ws = q.gain + (int64_t)warp_slot * T * Gain2<N, M>::CH2 * 32;
   int n_witer = 0, n_lanes = 0, n_rounds = 0, n_stores = 0;   // scheduling statistics of this warp (flushed once, at exit)
+  const bool solo_ok = Solo<N, M>::supported && Solo<N, M>::map(T, q.row_r4).bytes <= (int)sizeof(sm);
   for (;;) {
     // ------------------------------------------------ acquire
     int h = 0, take = 0;
@@ -410,6 +740,27 @@ WD void queue_warp_main(WarpRT &rt, const EnvSmall &e, const IlqrOpts &o, const 
         b = (int)(unsigned)(v & 0xffffffffull);
       }
     }
+    unsigned long long tp0 = 0, tp1 = 0, tp2 = 0, tp3 = 0;   // phase boundaries (trace only)
+    bool keep = false;
+    int nrounds = 0, n_taken = 0;
+    bool use_solo = false;
+    if constexpr (Solo<N, M>::supported) use_solo = solo_ok && take <= q.solo_max;
+    if (use_solo) {
+      // ------------------------------------------------ few problems: one after another, the whole warp on each (solo engine)
+      int iters = 0;
+      unsigned ns_lin = 0, ns_bwd = 0, ns_search = 0;
+      if constexpr (Solo<N, M>::supported)
+      for (int j = 0; j < take; j++) {
+        const int bj = rt.shfl(b, j);
+        const bool fj = rt.shfl((int)fresh, j) != 0, vj = rt.shfl((int)valid, j) != 0;
+        bool done_j = true;
+        if (vj) done_j = solo_run<KIND, N, M, QP>(rt, sm, e, o, q, bj, fj, take == 1, iters, n_taken, ns_lin, ns_bwd, ns_search);
+        if (lane == j) keep = valid && !done_j;
+      }
+      n_witer += iters; n_lanes += iters; n_rounds += iters; n_stores += n_taken;
+      // trace columns of a solo visit (rounds = 0): {linearise ns, backward ns, search ns, iterations of this visit}
+      tp0 = tr1 + ns_lin; tp1 = tp0 + ns_bwd; tp2 = tp1 + ns_search; tp3 = tp2 + (unsigned)iters;
+    } else {
     // ------------------------------------------------ state
     Prob p;
     prob_init(p);
@@ -429,6 +780,7 @@ WD void queue_warp_main(WarpRT &rt, const EnvSmall &e, const IlqrOpts &o, const 
     }
     if (rt.any(valid && fresh)) rt.fence();   // start_pass used plain stores; the staged reads are asynchronous copies issued by other lanes
     rt.syncwarp();
+    if (q.trace && lane == 0) tp0 = rt.now_ns();
 
     // ------------------------------------------------ backward (+ the retry wrapper _backward, ilqr.py:285-315)
     {
@@ -458,10 +810,11 @@ WD void queue_warp_main(WarpRT &rt, const EnvSmall &e, const IlqrOpts &o, const 
       }
     }
     rt.syncwarp();   // the gains of every lane are visible to the whole warp
+    if (q.trace && lane == 0) tp1 = rt.now_ns();
 
     // ------------------------------------------------ line search in rounds (_forward, ilqr.py:317-355)
     bool searching = valid && p.phase == PH_SEARCH, accept = false;
-    int next_ai = 0, chosen = 0, rollouts = 0, nrounds = 0;
+    int next_ai = 0, chosen = 0, rollouts = 0;
     real residual = 0;
     for (int round = 0; round < N_ALPHA + 1; round++) {
       const unsigned act_mask = rt.ballot(searching);
@@ -502,17 +855,19 @@ WD void queue_warp_main(WarpRT &rt, const EnvSmall &e, const IlqrOpts &o, const 
     // store pass: the candidate that becomes the nominal -- accepted, or rejected but converged by residual (ilqr.py:253-257)
     const bool take_cand = valid && p.phase == PH_SEARCH && (accept || residual < o.atol);
     const unsigned take_mask = rt.ballot(take_cand);
+    if (q.trace && lane == 0) tp2 = rt.now_ns();
     if (take_mask) {
       real J, res;
       rollout_round<KIND, N, M, true>(rt, sm, e, T, NH, take_mask, lane, take_cand, o.alphas[take_cand ? chosen : 0], gain_ws, J, res);
       nrounds++;
     }
+    if (q.trace && lane == 0) tp3 = rt.now_ns();
     if (valid && p.phase == PH_SEARCH && tick_finish(o, accept, residual, rollouts, p)) p.cur ^= 1;   // ilqr.py:253-270
 
-    // ------------------------------------------------ results / re-queue
+    // ------------------------------------------------ results
     rt.fence();      // trajectory lines were written by other lanes of the warp (and must be visible grid-wide before the ticket is)
     rt.syncwarp();
-    const bool keep = valid && p.phase != PH_DONE;
+    keep = valid && p.phase != PH_DONE;
     if (valid && !keep) {   // finished: results in the reference layouts (states [B,T+1,n], actions [B,T,m], costs [B,T+1])
       const VecTraj<N, M> nom = {traj_row(q, p.cur, b), CHn, 1};
       real *S = q.states + (int64_t)b * (T + 1) * N, *A = q.actions + (int64_t)b * T * M, *Cc = q.costs + (int64_t)b * (T + 1);
@@ -537,6 +892,9 @@ WD void queue_warp_main(WarpRT &rt, const EnvSmall &e, const IlqrOpts &o, const 
       s.mu = p.mu; s.delta = p.delta; s.iteration = p.iteration; s.n_bwd = p.n_bwd; s.n_fwd = p.n_fwd; s.cg = (p.cur & 1) | (p.guard << 1);
       q.prob[b] = s;
     }
+    n_witer++; n_lanes += take; n_rounds += nrounds; n_stores += popc32(take_mask);
+    }
+    // ------------------------------------------------ re-queue the problems that go on, count the finished ones
     const unsigned km = rt.ballot(keep), dm = rt.ballot(valid && !keep);
     rt.fence();
     rt.syncwarp();
@@ -552,13 +910,13 @@ WD void queue_warp_main(WarpRT &rt, const EnvSmall &e, const IlqrOpts &o, const 
     }
     rt.syncwarp();
     if (lane == 0 && km) rt.atomic_add(q.ctrl + C_COUNT, popc32(km));   // credit the semaphore once the tickets are published
-    n_witer++; n_lanes += take; n_rounds += nrounds; n_stores += popc32(take_mask);
     if (q.trace && lane == 0) {
       const int slot = rt.atomic_add(q.ctrl + C_TRACE, 1);
       if (slot < q.trace_cap) {
-        unsigned *r = q.trace + (int64_t)slot * 4;
+        unsigned *r = q.trace + (int64_t)slot * 8;
         r[0] = (unsigned)tr0; r[1] = (unsigned)(tr1 - tr0); r[2] = (unsigned)(rt.now_ns() - tr1);
         r[3] = (unsigned)take | ((unsigned)nrounds << 8) | ((unsigned)warp_slot << 16);
+        r[4] = (unsigned)(tp0 - tr1); r[5] = (unsigned)(tp1 - tp0); r[6] = (unsigned)(tp2 - tp1); r[7] = (unsigned)(tp3 - tp2);
       }
     }
   }

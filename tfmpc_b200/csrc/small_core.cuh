@@ -279,59 +279,6 @@ HD int boxqp(const real *H, const real *q, const real *lo, const real *hi, real 
 }
 
 
-// Closed-form box-QP for M <= 2 (QP_CLOSED).  NOT the reference's iteration: it returns the exact minimiser of the
-// strictly convex QP over the box, which is what optimization.py:6-101 converges to (the projected-Newton loop stops on
-// a relative decrease < 1e-8 or a free-gradient norm < 1e-6), without the data-dependent loop: ~90 instructions against
-// ~1,400 for the iteration in the navigation workload, and no divergence.  The free / clamped flags, the failure rule
-// (full H not positive definite at the first factorisation, :37-51) and the factor handed to the K solve follow the
-// reference's definitions (:121-127, ilqr.py:375-383) evaluated at the solution.
-// Why two candidates suffice for M = 2: with xu the unconstrained minimiser, the box minimiser lies on an edge whose
-// bound xu violates (KKT on a non-violated edge's interior forces x = xu there), i.e. at (b0, clip(argmin_x1 f(b0, .)))
-// or (clip(argmin_x0 f(., b1)), b1) with b = clip(xu); when both bounds are violated the lower objective wins.
-// Parity: same iteration count as the fp64 oracle on >= 99.9 % of C3 problems, fp32 inside the fp32-vs-fp64 noise band
-// (tests/test_device_logic_emulation.py::test_closed_form_qp_*; DESIGN.md section 3).
-template <int M>
-HD int boxqp_closed(const real *H, const real *q, const real *lo, const real *hi, real *x, real *L, bool *fr) {
-  static_assert(M <= 2, "closed-form box-QP: M <= 2");
-  const real eps = (real)1e-6;
-#pragma unroll
-  for (int i = 0; i < M; i++) fr[i] = true;
-  if (chol_masked<M>(H, fr, L)) return 2;  // x stays at the start point, as in the reference
-  real xu[M];
-#pragma unroll
-  for (int i = 0; i < M; i++) xu[i] = q[i];
-  chol_solve<M>(L, xu);
-#pragma unroll
-  for (int i = 0; i < M; i++) xu[i] = -xu[i];
-  if (M == 1) {
-    x[0] = r_clip(xu[0], lo[0], hi[0]);
-  } else {
-    const real b0 = r_clip(xu[0], lo[0], hi[0]), b1 = r_clip(xu[1], lo[1], hi[1]);
-    const bool v0 = xu[0] != b0, v1 = xu[1] != b1;
-    real xa[2], xb[2];
-    xa[0] = b0; xa[1] = r_clip(-(q[1] + H[2] * b0) / H[3], lo[1], hi[1]);
-    xb[1] = b1; xb[0] = r_clip(-(q[0] + H[1] * b1) / H[0], lo[0], hi[0]);
-    bool takeA = v0;
-    if (v0 && v1) takeA = qp_value<2>(H, q, xa) <= qp_value<2>(H, q, xb);
-    const bool inside = !v0 && !v1;
-    x[0] = inside ? xu[0] : (takeA ? xa[0] : xb[0]);
-    x[1] = inside ? xu[1] : (takeA ? xa[1] : xb[1]);
-  }
-  bool any_c = false;
-#pragma unroll
-  for (int i = 0; i < M; i++) {  // :121-127 at the solution
-    real s = 0;
-#pragma unroll
-    for (int j = 0; j < M; j++) s += H[i * M + j] * x[j];
-    const real g = q[i] + s;
-    const bool c = (r_abs(x[i] - lo[i]) < eps && g > 0) || (r_abs(hi[i] - x[i]) < eps && g < 0);
-    fr[i] = !c;
-    any_c = any_c || c;
-  }
-  if (any_c) chol_masked<M>(H, fr, L);  // factor of H[free,free]; cannot fail when the full H is positive definite
-  return 0;
-}
-
 enum { QP_NEWTON = 0, QP_COOP = 1, QP_CLOSED = 2 };  // box-QP flavour of the constrained controller
 
 #ifdef __CUDACC__
@@ -488,17 +435,28 @@ struct Traits {
   static constexpr bool lxx_diag = true, luu_diag = true, lxu_zero = true;
 };
 
-// tfmpc/solvers/ilqr.py:108-170 with the controllers of :357-387.  V_x, V_xx, J, dV1, dV2 are
-// carried across timesteps.  Returns 0, 1 (unconstrained Cholesky failed) or 2 (box-QP failed).
-// QP = QP_COOP: called by all 32 lanes of a warp in lock step (device only); the box-QP then runs warp-cooperatively.
-// QP = QP_CLOSED (M <= 2): the closed-form box-QP above instead of the reference's iteration.
-template <int KIND, int N, int M, int QP = QP_NEWTON>
-HD int backward_step(const EnvSmall &e, const Lin<N, M> &L, const real *u, real mu, real *V_x, real *V_xx, real &J, real &dV1,
-                     real &dV2, real *K, real *k) {
+// The Q block of one timestep (ilqr.py:122-134) as one flat array, so that the warp-cooperative ("solo") backward of
+// queue_core.cuh can hand it from the lanes that assemble it to the lanes that consume it through shared memory.
+template <int N, int M>
+struct QB {
+  static constexpr int OX = 0, OU = N, OXX = N + M, OUU = OXX + N * N, OUX = OUU + M * M, OUUR = OUX + M * N, OUXR = OUUR + M * M,
+                       SIZE = OUXR + M * N;
+  real v[SIZE];
+  HD real *Q_x() { return v + OX; }
+  HD real *Q_u() { return v + OU; }
+  HD real *Q_xx() { return v + OXX; }
+  HD real *Q_uu() { return v + OUU; }
+  HD real *Q_ux() { return v + OUX; }
+  HD real *Q_uu_reg() { return v + OUUR; }
+  HD real *Q_ux_reg() { return v + OUXR; }
+};
+
+// ---- stage 1: Q_x, Q_u (:122-123), Q_xx, Q_uu, Q_ux (:129-131) and the state-regularised Q_uu_reg, Q_ux_reg (:127,133-134)
+template <int KIND, int N, int M>
+HD void assemble_q(const Lin<N, M> &L, real mu, const real *V_x, const real *V_xx, QB<N, M> &q) {
   typedef Traits<KIND> TR;
-  real Q_x[N], Q_u[M], Q_xx[N * N], Q_uu[M * M], Q_ux[M * N], Q_uu_reg[M * M], Q_ux_reg[M * N];
+  real *Q_x = q.Q_x(), *Q_u = q.Q_u(), *Q_xx = q.Q_xx(), *Q_uu = q.Q_uu(), *Q_ux = q.Q_ux(), *Q_uu_reg = q.Q_uu_reg(), *Q_ux_reg = q.Q_ux_reg();
   real fxTV[N * N], fuTV[M * N], fuTVr[M * N];
-  int status = 0;
 #pragma unroll
   for (int i = 0; i < N; i++) {  // :122
     real s = 0;
@@ -584,6 +542,85 @@ HD int backward_step(const EnvSmall &e, const Lin<N, M> &L, const real *u, real 
       Q_ux_reg[i * N + j] = TR::lxu_zero ? sr : L.l_xu[j * M + i] + sr;
     }
   }
+}
+
+// Closed-form constrained controller for M <= 2 (QP_CLOSED): box-QP solution k AND feedback gain K in one go.
+// NOT the reference's iteration: k is the exact minimiser of the strictly convex QP over the box, which is what
+// optimization.py:6-101 converges to (the projected-Newton loop stops on a relative decrease < 1e-8 or a free-gradient
+// norm < 1e-6), without the data-dependent loop and without a Cholesky factor.
+// Why two candidates suffice for M = 2: with xu the unconstrained minimiser, the box minimiser lies on an edge whose
+// bound xu violates (KKT on a non-violated edge's interior forces x = xu there), i.e. at (b0, clip(argmin_x1 f(b0, .)))
+// or (clip(argmin_x0 f(., b1)), b1) with b = clip(xu); when both bounds are violated the lower objective wins.
+// The free / clamped flags follow optimization.py:121-127 evaluated at the solution; the factorisation-failure rule of
+// :37-51 (a non-positive Cholesky pivot of the full H) is the equivalent "h00 <= 0 or det <= 0";
+// K[free rows] = -H_ff^-1 Q_ux_reg[free] (ilqr.py:375-383) uses the adjugate inverse when both rows are free and a plain
+// reciprocal when one is.  The three reciprocals are independent of each other, so the whole controller is ~70
+// instructions with a dependent chain of one reciprocal + ~25 FMA-class operations (the Cholesky + triangular solves of
+// the generic path chain four divisions and two square roots per solve; the iteration costs ~1,400 instructions).
+// Returns 0, or 2 when H is not positive definite (k stays at the start point, K = 0, as in the reference).
+// Parity: same iteration count as the fp64 oracle on >= 99 % of C3 problems, fp32 inside the fp32-vs-fp64 noise band
+// (tests/test_device_logic_emulation.py::test_closed_form_qp_*; DESIGN.md section 3).
+template <int N, int M>
+HD int controller_closed(const real *H, const real *q, const real *lo, const real *hi, const real *B, real *k, real *K) {
+  static_assert(M <= 2, "closed-form controller: M <= 2");
+  const real eps = (real)1e-6;
+  if (M == 1) {
+    const real h = H[0];
+    if (!(h > 0)) {
+#pragma unroll
+      for (int j = 0; j < N; j++) K[j] = 0;
+      return 2;
+    }
+    const real r = (real)1 / h;
+    const real x = r_clip(-(q[0] * r), lo[0], hi[0]);
+    const real g = q[0] + h * x;
+    const bool c = (r_abs(x - lo[0]) < eps && g > 0) || (r_abs(hi[0] - x) < eps && g < 0);
+    k[0] = x;
+#pragma unroll
+    for (int j = 0; j < N; j++) K[j] = c ? (real)0 : -(B[j] * r);
+    return 0;
+  } else {
+    const real h00 = H[0], h01 = H[1], h10 = H[2], h11 = H[3];
+    const real det = h00 * h11 - h10 * h10;
+    if (!(h00 > 0) || !(det > 0)) {
+#pragma unroll
+      for (int i = 0; i < M * N; i++) K[i] = 0;
+      return 2;
+    }
+    const real rd = (real)1 / det, r0 = (real)1 / h00, r1 = (real)1 / h11;
+    const real xu0 = -((h11 * q[0] - h10 * q[1]) * rd), xu1 = -((h00 * q[1] - h10 * q[0]) * rd);
+    const real b0 = r_clip(xu0, lo[0], hi[0]), b1 = r_clip(xu1, lo[1], hi[1]);
+    const bool v0 = xu0 != b0, v1 = xu1 != b1;
+    real xa[2], xb[2];
+    xa[0] = b0; xa[1] = r_clip(-((q[1] + h10 * b0) * r1), lo[1], hi[1]);
+    xb[1] = b1; xb[0] = r_clip(-((q[0] + h01 * b1) * r0), lo[0], hi[0]);
+    bool takeA = v0;
+    if (v0 && v1) takeA = qp_value<2>(H, q, xa) <= qp_value<2>(H, q, xb);
+    const bool inside = !v0 && !v1;
+    const real x0 = inside ? xu0 : (takeA ? xa[0] : xb[0]), x1 = inside ? xu1 : (takeA ? xa[1] : xb[1]);
+    const real g0 = q[0] + (h00 * x0 + h01 * x1), g1 = q[1] + (h10 * x0 + h11 * x1);
+    const bool c0 = (r_abs(x0 - lo[0]) < eps && g0 > 0) || (r_abs(hi[0] - x0) < eps && g0 < 0);   // optimization.py:121-127 at the solution
+    const bool c1 = (r_abs(x1 - lo[1]) < eps && g1 > 0) || (r_abs(hi[1] - x1) < eps && g1 < 0);
+    k[0] = x0; k[1] = x1;
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+      const real B0 = B[j], B1 = B[N + j];
+      const real f0 = -((h11 * B0 - h10 * B1) * rd), f1 = -((h00 * B1 - h10 * B0) * rd);   // both rows free
+      K[j] = c0 ? (real)0 : (c1 ? -(B0 * r0) : f0);
+      K[N + j] = c1 ? (real)0 : (c0 ? -(B1 * r1) : f1);
+    }
+    return 0;
+  }
+}
+
+// ---- stage 2: the controller, ilqr.py:136-143 -> :357-362 (unconstrained) / :364-387 (constrained) / :139-141 (bang-bang).
+// Returns 0, 1 (unconstrained Cholesky failed) or 2 (box-QP failed).  V_xx is the value function BEFORE this step's update.
+// QP = QP_COOP: called by all 32 lanes of a warp in lock step (device only); the box-QP then runs warp-cooperatively.
+// QP = QP_CLOSED (M <= 2): the closed-form controller above instead of the reference's iteration.
+template <int KIND, int N, int M, int QP>
+HD int controller(const EnvSmall &e, QB<N, M> &q, const real *V_xx, const real *u, real *K, real *k) {
+  real *Q_u = q.Q_u(), *Q_uu_reg = q.Q_uu_reg(), *Q_ux_reg = q.Q_ux_reg();
+  int status = 0;
   if (e.bounded) {  // :136
     bool any_nz = false;
 #pragma unroll
@@ -595,15 +632,23 @@ HD int backward_step(const EnvSmall &e, const Lin<N, M> &L, const real *u, real 
     real lo[M], hi[M], Lf[M * M];
     bool fr[M];
     int st = 0;
-    if (enter_qp) {  // :137-138 -> _get_constrained_controller :364-387
+    if constexpr (QP == QP_CLOSED && M <= 2) {
+      if (any_nz) {  // :137-138 -> _get_constrained_controller :364-387
 #pragma unroll
-      for (int i = 0; i < M; i++) { lo[i] = e.low[i] - u[i]; hi[i] = e.high[i] - u[i]; k[i] = (lo[i] + hi[i]) / (real)2; }
+        for (int i = 0; i < M; i++) { lo[i] = e.low[i] - u[i]; hi[i] = e.high[i] - u[i]; k[i] = (lo[i] + hi[i]) / (real)2; }
+        if (controller_closed<N, M>(Q_uu_reg, Q_u, lo, hi, Q_ux_reg, k, K)) status = 2;
+        return status;
+      }
+    } else {
+      if (enter_qp) {  // :137-138 -> _get_constrained_controller :364-387
+#pragma unroll
+        for (int i = 0; i < M; i++) { lo[i] = e.low[i] - u[i]; hi[i] = e.high[i] - u[i]; k[i] = (lo[i] + hi[i]) / (real)2; }
 #ifdef __CUDA_ARCH__
-      if (QP == QP_COOP) st = boxqp_warp<M>(any_nz, e.qp_steps, e.qp_klast, Q_uu_reg, Q_u, lo, hi, k, Lf, fr);
-      else
+        if (QP == QP_COOP) st = boxqp_warp<M>(any_nz, e.qp_steps, e.qp_klast, Q_uu_reg, Q_u, lo, hi, k, Lf, fr);
+        else
 #endif
-      if constexpr (QP == QP_CLOSED && M <= 2) st = boxqp_closed<M>(Q_uu_reg, Q_u, lo, hi, k, Lf, fr);
-      else st = boxqp<M>(Q_uu_reg, Q_u, lo, hi, k, Lf, fr);
+        st = boxqp<M>(Q_uu_reg, Q_u, lo, hi, k, Lf, fr);
+      }
     }
     if (any_nz) {
       if (st) status = 2;
@@ -643,7 +688,13 @@ HD int backward_step(const EnvSmall &e, const Lin<N, M> &L, const real *u, real 
       for (int i = 0; i < M; i++) K[i * N + j] = -col[i];
     }
   }
-  // value update with the UNregularised Q, :145-162
+  return status;
+}
+
+// ---- stage 3: value update with the UNregularised Q (:145-162), J (:164), dV1, dV2 (:166-167)
+template <int N, int M>
+HD void value_update(QB<N, M> &q, const real *K, const real *k, real l, real *V_x, real *V_xx, real &J, real &dV1, real &dV2) {
+  const real *Q_x = q.Q_x(), *Q_u = q.Q_u(), *Q_xx = q.Q_xx(), *Q_uu = q.Q_uu(), *Q_ux = q.Q_ux();
   real KtQuu[N * M];
 #pragma unroll
   for (int i = 0; i < N; i++)
@@ -673,7 +724,7 @@ HD int backward_step(const EnvSmall &e, const Lin<N, M> &L, const real *u, real 
   for (int i = 0; i < N; i++)
 #pragma unroll
     for (int j = 0; j < N; j++) V_xx[i * N + j] = (real)0.5 * (Vn[i * N + j] + Vn[j * N + i]);  // :162
-  J += L.l;  // :164
+  J += l;  // :164
   real d1 = 0, d2 = 0;
 #pragma unroll
   for (int i = 0; i < M; i++) d1 += k[i] * Q_u[i];
@@ -686,6 +737,18 @@ HD int backward_step(const EnvSmall &e, const Lin<N, M> &L, const real *u, real 
     d2 += s * k[j];
   }
   dV2 += (real)0.5 * d2;  // :167
+}
+
+// tfmpc/solvers/ilqr.py:108-170 with the controllers of :357-387: the three stages above for one timestep in one thread.
+// V_x, V_xx, J, dV1, dV2 are carried across timesteps.  Returns 0, 1 (unconstrained Cholesky failed) or 2 (box-QP failed).
+template <int KIND, int N, int M, int QP = QP_NEWTON>
+HD int backward_step(const EnvSmall &e, const Lin<N, M> &L, const real *u, real mu, real *V_x, real *V_xx, real &J, real &dV1,
+                     real &dV2, real *K, real *k) {
+  QB<N, M> q;
+  assemble_q<KIND, N, M>(L, mu, V_x, V_xx, q);
+  const int status = controller<KIND, N, M, QP>(e, q, V_xx, u, K, k);
+  if (status == 1) return 1;
+  value_update<N, M>(q, K, k, L.l, V_x, V_xx, J, dV1, dV2);
   return status;
 }
 

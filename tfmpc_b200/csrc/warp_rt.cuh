@@ -9,6 +9,7 @@
 
 #ifdef __CUDACC__
 #define WD __device__ __forceinline__
+#define WD_NOINLINE __device__ __noinline__
 
 struct WarpRT {
   int lane;
@@ -62,6 +63,7 @@ struct WarpRT {
 #include <string.h>
 #include <time.h>
 #define WD inline
+#define WD_NOINLINE inline
 
 struct WarpShared {   // one per emulated warp
   pthread_barrier_t bar;

@@ -270,9 +270,10 @@ def queue_counters(workspace, precision="f32"):
 
 
 def queue_trace(env, B, T, workspace, max_records=1 << 18):
-    """tfmpc_ilqr_queue_trace -> int64 array [records, 4] (acquire start ns (low 32 bits), wait ns, work ns, packed lanes/rounds/warp)."""
+    """tfmpc_ilqr_queue_trace -> int64 array [records, 8] (acquire start ns (low 32 bits), wait ns, work ns, packed lanes/rounds/warp,
+    set-up ns, backward ns, search ns, store-pass ns)."""
     import numpy as np
-    out = np.zeros((max_records, 4), dtype=np.uint32)
+    out = np.zeros((max_records, 8), dtype=np.uint32)
     env.lib.tfmpc_ilqr_queue_trace.restype = C.c_int64
     n = env.lib.tfmpc_ilqr_queue_trace(env.handle, C.c_int64(B), int(T), C.c_void_p(workspace.data_ptr()), out.ctypes.data_as(C.c_void_p),
                                        C.c_int64(max_records), N.stream_ptr())

@@ -12,8 +12,11 @@ A "step" is one pass of the hot path over one batch: iLQR.solve of B independent
 the reference's outer loop ilqr.py:227-277 (linearise + >= 1 backward pass + line search), summed over
 problems.  Workload (default): BASELINE config C3 -- nonlinear 2-D navigation with two deceleration zones,
 H = 50, B = 65,536 problems PER GPU (weak scaling: the batch is sharded, no data-path collective; with
-N > 1 ranks the per-problem costs and iteration counts resident at the end are all-gathered over NCCL once, inside
-the timed region).
+N > 1 ranks the full results -- states, actions, costs, iteration counts -- of the batch resident at the end are all-gathered
+over NCCL, one collective per buffer, inside the timed region).  The line also carries
+  parity          CUDA against the oracle on the WHOLE timed batch (rank 0's 65,536 problems; N = 1 only)
+  extra.strong    the same global batch of 65,536 problems CUT over the N ranks (sharding.solve_sharded), full gather timed
+  extra.workloads short runs of BASELINE configs C2, C4, C5 (single solve) and C5 (MPC loop), each with roofline and CPU baseline
 Prints ONE JSON line (rank 0).
 """
 import argparse
@@ -129,24 +132,60 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
 
 
-def cpu_baseline(name, T, sample, threads=0, repeats=1):
+def cpu_baseline(name, T, sample, threads=0, repeats=1, want_result=False):
     """The CPU arm: the oracle port (C, OpenMP over problems) on the host cores, on a bounded sample of the
-    same workload.  Returns (problem-iterations/s, cores, problem-iterations, seconds)."""
+    same workload -- the first `sample` problems of the GPU arm's rank-0 batch.  Returns (problem-iterations/s, cores,
+    problem-iterations, seconds[, oracle result])."""
     from oracle import oracle
     o = oracle.Oracle("f32")
     cfg = workload_cfg(name)
-    x0, u0 = make_inputs(cfg, sample, T, seed=12345)
+    x0, u0 = make_inputs(cfg, sample, T, seed=1000)
     env = o.make_env(cfg)
     cores = max(o.max_threads(), len(os.sched_getaffinity(0))) if threads <= 0 else threads   # every host core the process may use
-    best = None
+    best, res = None, None
     for _ in range(repeats):
         t0 = time.perf_counter()
         r = o.ilqr_solve(env, x0, u0, nthreads=cores)
         dt = time.perf_counter() - t0
         pi = float((r["iterations"] + 1).sum())
         if best is None or dt < best[1]:
-            best = (pi, dt)
-    return best[0] / best[1], cores, best[0], best[1]
+            best, res = (pi, dt), r
+    out = (best[0] / best[1], cores, best[0], best[1])
+    return out + (res,) if want_result else out
+
+
+def cpu_mpc_loop(T, sample, threads=0):
+    """CPU arm of C5 (MPC loop): the shrinking-horizon loop of agents/mpc.py:10-15 + runners/__init__.py:14-43 driven with the oracle
+    as the solver, `sample` plants.  Returns (problem-iterations/s, cores, problem-iterations, seconds)."""
+    from oracle import oracle
+    o = oracle.Oracle("f32")
+    cfg = workload_cfg("c5")
+    env = o.make_env(cfg)
+    cores = max(o.max_threads(), len(os.sched_getaffinity(0))) if threads <= 0 else threads
+    state = make_inputs(cfg, sample, T, seed=1000)[0]
+    pi = 0.0
+    t0 = time.perf_counter()
+    for t in range(T):
+        u0 = make_inputs(cfg, sample, T - t, seed=2000 + t)[1]
+        r = o.ilqr_solve(env, state, u0, nthreads=cores)
+        pi += float((r["iterations"] + 1).sum())
+        state = o.env_eval(env, state, r["actions"][:, 0])[0].astype(np.float32)
+    dt = time.perf_counter() - t0
+    return pi / dt, cores, pi, dt
+
+
+def parity_block(stats, total, r):
+    """CUDA against the oracle on the same problems: the north-star gate (converged cost within 1e-4 relative, same iteration count)
+    as fractions of the batch."""
+    n = len(r["iterations"])
+    d = np.abs(stats[:n, 0].astype(np.int64) - r["iterations"])
+    tot_r = r["costs"].sum(1).astype(np.float64)
+    relc = np.abs(total[:n].astype(np.float64) - tot_r) / np.maximum(np.abs(tot_r), 1e-30)
+    return {"problems": int(n), "same_iterations": float(np.mean(d == 0)), "within1": float(np.mean(d <= 1)),
+            "cost_within_1e-4": float(np.mean(relc <= 1e-4)), "cost_within_1e-4_given_same_iterations": float(np.mean(relc[d == 0] <= 1e-4)),
+            "status_match": float(np.mean(stats[:n, 3] == r["status"])),
+            "against": "the fp32 oracle (oracle/, C restatement of the reference) on the same inputs; two correct fp32 implementations of "
+                       "this algorithm agree on ~96 % of iteration counts (threshold decisions), the fp64 build is exact -- tests/test_gpu_queue.py"}
 
 
 def reference_under_shim(name, T, problems=3):
@@ -175,23 +214,32 @@ def reference_under_shim(name, T, problems=3):
             "iterations": d["iterations"]}
 
 
+def arm_config(name, B, world):
+    """The `config` object BOTH arms print (the driver compares them): what is solved, not how."""
+    desc, _, T = WORKLOADS[name]
+    dims = {"c2": (2, 2), "c3": (2, 2), "c4": (20, 20), "c5s": (32, 32), "c5": (32, 32)}[name]
+    return {"workload": desc, "batch_per_gpu": int(B), "global_batch": int(B) * int(world), "horizon": T, "state_dim": dims[0], "action_dim": dims[1],
+            "solver": ("LQR: backward Riccati sweep + forward rollout (lqr.py:59-161)" if name == "c2" else
+                       "iLQR, reference defaults atol=5e-3 max_iterations=100 mu_min=1e-6 delta_0=2 c1=0 alpha_min=1e-3")}
+
+
 def c2_inputs(B, seed):
     rng = np.random.RandomState(seed)
     return rng.uniform(-10, 10, size=(B, 2)).astype(np.float32), rng.normal(size=(B, 2)).astype(np.float32)
 
 
-def c2_cpu(B, T, threads=0):
-    """CPU arm of C2: the oracle's LQR (C, OpenMP over problems).  Returns (problems/s, cores, seconds)."""
+def c2_cpu(B, T, threads=0, want_result=False):
+    """CPU arm of C2: the oracle's LQR (C, OpenMP over problems) on the GPU arm's rank-0 inputs.  Returns (problems/s, cores, seconds[, result])."""
     from oracle import oracle
     o = oracle.Oracle("f32")
-    goal, x0 = c2_inputs(B, 12345)
+    goal, x0 = c2_inputs(B, 1000)
     F = np.concatenate([np.eye(2), np.eye(2)], axis=1)
     c = np.concatenate([-2 * goal, np.zeros_like(goal)], axis=1)
     cores = max(o.max_threads(), len(os.sched_getaffinity(0))) if threads <= 0 else threads   # every host core the process may use
     t0 = time.perf_counter()
-    o.lqr_solve(F, np.zeros(2), np.diag([2.0, 2.0, 10.0, 10.0]), c, x0, T, nthreads=cores)
+    r = o.lqr_solve(F, np.zeros(2), np.diag([2.0, 2.0, 10.0, 10.0]), c, x0, T, nthreads=cores)
     dt = time.perf_counter() - t0
-    return B / dt, cores, dt
+    return (B / dt, cores, dt, r) if want_result else (B / dt, cores, dt)
 
 
 def run_c2(args):
@@ -272,12 +320,13 @@ def run_c2(args):
             traffic, traffic_src = tr["dram_bytes_per_problem"] * B, tr["source"]
         line = {"metric": "batched LQR problems/sec", "value": value, "unit": "problems/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-                "data": "synthetic",
-                "config": {"workload": desc, "batch_per_gpu": B, "global_batch": B * world, "horizon": T, "state_dim": 2, "action_dim": 2,
-                           "parallelism": f"batch sharded over {world} GPU(s), no data-path collective",
-                           "l2": "256 MB buffer written between timed iterations (untimed L2 flush)",
-                           "status_nonzero": int((out["status"] != 0).sum())},
-                "step_ms": step_ms,
+                "data": "synthetic", "config": arm_config("c2", B, world),
+                "details": {"parallelism": f"batch sharded over {world} GPU(s), no data-path collective",
+                            "l2": "256 MB buffer written between timed iterations (untimed L2 flush)",
+                            "status_nonzero": int((out["status"] != 0).sum()), "step_ms": step_ms,
+                            "floor": "at 65,536 problems one launch moves 50 MB: 7.6 us at the HBM peak against ~3 us of launch + ramp-up and a "
+                                     "2,048-CTA grid that is 1.7 waves of 8 CTAs/SM -- the kernel reaches 66 % of the HBM peak at 1,048,576 problems "
+                                     "(profiles/r01_bench_c2_lqr_staged_1M.json)"},
                 "roofline": {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
                              "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                              "kernel": "k_lqr_small_staged<2,2> (thread per problem, backward + forward fused, TMA bulk stores)",
@@ -286,64 +335,77 @@ def run_c2(args):
                         "d2h_bytes_per_step": int(sum(v.numel() * 4 for v in ho.values())), "api": "tfmpc_lqr_solve_host (pinned host buffers in and out, synchronous), one call per step"},
                 "gpu_launches": int(launches), "clocks": clocks}
         if world == 1 and not args.no_cpu_baseline:
-            v, cores, dt = c2_cpu(args.cpu_sample or B, T)
+            nb = args.cpu_sample or B
+            v, cores, dt, res = c2_cpu(nb, T, want_result=True)
             line["cpu_baseline"] = {"value": v, "unit": "problems/s", "cores": cores, "kind": "port",
-                                    "sample": f"{args.cpu_sample or B} problems in {dt:.2f} s, C/OpenMP restatement of reference LQR (oracle/)"}
+                                    "sample": f"the first {nb} problems of the timed batch in {dt:.2f} s, C/OpenMP restatement of reference LQR (oracle/)"}
+            if nb == B:
+                errs = {k: float(np.max(np.abs(out[k].cpu().numpy() - res[k])) / max(1.0, float(np.max(np.abs(res[k])))))
+                        for k in ("states", "actions", "costs", "K", "k", "V", "v", "const")}
+                line["parity"] = {"problems": int(B), "max_rel_error": errs, "within_1e-5": bool(max(errs.values()) < 1e-5),
+                                  "against": "the fp32 oracle (oracle/) on the same inputs; north-star gate 1e-5 relative"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
 def run_reference(args):
+    """The CPU arm: the reference's algorithm for this path on the box's host cores (the C/OpenMP restatement under oracle/ -- the
+    TensorFlow reference itself is not installable offline --, every host thread), same workload, metric and config as the GPU
+    arm; each step is a bounded sample of the workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    desc, _, T = WORKLOADS[args.workload]
-    if args.workload == "c2":
-        B = args.cpu_sample or args.batch or WORKLOADS["c2"][1]
+    name = args.workload
+    desc, B_full, T = WORKLOADS[name]
+    B_full = args.batch or B_full
+    cfg_line = arm_config(name, B_full, args.gpus)
+    if name == "c2":
+        B = args.cpu_sample or B_full
         for _ in range(args.warmup):
             c2_cpu(B, T)
         secs = 0.0
         for _ in range(args.steps):
             v, cores, dt = c2_cpu(B, T)
             secs += dt
-        value = B * args.steps / secs
-        print(json.dumps({"impl": "reference", "metric": "batched LQR problems/sec", "value": value, "unit": "problems/s", "n_gpus": args.gpus,
-                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True,
-                          "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                          "config": {"workload": desc, "batch_per_step": B, "horizon": T},
-                          "cpu_baseline": {"value": value, "unit": "problems/s", "cores": cores, "kind": "port",
-                                           "sample": f"{B} problems per step, {args.steps} steps"},
-                          "e2e": {"value": value, "unit": "problems/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}), flush=True)
-        return
-    sample = args.cpu_sample or {"c3": 65536, "c4": 512, "c5s": 128, "c5": 128}[args.workload]
-    for _ in range(args.warmup):
-        cpu_baseline(args.workload, T, max(64, sample // 8))
-    vals, secs, pis = [], 0.0, 0.0
-    for _ in range(args.steps):
-        v, cores, pi, dt = cpu_baseline(args.workload, T, sample)
-        vals.append(v); secs += dt; pis += pi
-    value = pis / secs
-    line = {"impl": "reference", "metric": "batched iLQR problem-iterations/sec", "value": value, "unit": "problem-iterations/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": desc, "batch_per_step": sample, "horizon": T,
-                       "note": "CPU arm = this repo's C/OpenMP restatement of the reference algorithm (oracle/); the TensorFlow "
-                               "reference itself is not installable offline"},
-            "cpu_baseline": {"value": value, "unit": "problem-iterations/s", "cores": cores, "kind": "port",
-                             "sample": f"{sample} problems of the workload per step, {args.steps} steps"},
-            "e2e": {"value": value, "unit": "problem-iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
-    if args.workload == "c3":
-        line["reference_under_shim"] = reference_under_shim(args.workload, T)
+        value, unit, metric = B * args.steps / secs, "problems/s", "batched LQR problems/sec"
+        sample = f"{B} problems per step, {args.steps} steps"
+    else:
+        sample_n = args.cpu_sample or {"c3": B_full, "c4": 512, "c5s": 128, "c5": 16}[name]
+        run = (lambda n: cpu_mpc_loop(T, n)) if name == "c5" else (lambda n: cpu_baseline(name, T, n))
+        for _ in range(args.warmup):
+            run(max(8 if name == "c5" else 64, sample_n // 8))
+        secs, pis = 0.0, 0.0
+        for _ in range(args.steps):
+            v, cores, pi, dt = run(sample_n)
+            secs += dt; pis += pi
+        value, unit, metric = pis / secs, "problem-iterations/s", "batched iLQR problem-iterations/sec"
+        sample = f"{sample_n} problems of the workload per step, {args.steps} steps"
+    line = {"impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": cfg_line,
+            "details": {"note": "CPU arm = this repo's C/OpenMP restatement of the reference algorithm (oracle/), one problem per thread; the "
+                                "TensorFlow reference itself is not installable offline (DESIGN.md section 2)"},
+            "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    if name == "c3":
+        line["reference_under_shim"] = reference_under_shim(name, T)
     print(json.dumps(line), flush=True)
+
+
+def traffic_file(name):
+    for rnd in ("r02", "r01"):
+        path = os.path.join(ROOT, "profiles", f"{rnd}_traffic_{name}.json")
+        if os.path.exists(path):
+            return json.load(open(path))
+    return None
 
 
 def run_ours(args):
     import torch
     import torch.distributed as dist
 
-    from tfmpc_b200 import _native, envs, ops
+    from tfmpc_b200 import _native, envs, ops, sharding
     from tfmpc_b200.solvers.ilqr import iLQR
 
     rank = int(os.environ.get("RANK", "0"))
@@ -353,10 +415,11 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    desc, B, T = WORKLOADS[args.workload]
+    name = args.workload
+    desc, B, T = WORKLOADS[name]
     if args.batch:
         B = args.batch
-    cfg = workload_cfg(args.workload)
+    cfg = workload_cfg(name)
     env = envs.make_env(cfg)
     solver = iLQR(env)
     n, m = env.state_size, env.action_size
@@ -365,107 +428,84 @@ def run_ours(args):
     x0, u0 = x0_pin.to(dev), u0_pin.to(dev)
     S = max(1, min(args.streams, args.steps))
     nat, opts = env.native(), solver._opts()
+    queue_path = name == "c3" and os.environ.get("TFMPC_SOLVER", "queue") != "ticks"
 
-    def new_out(host=False):
+    def new_out(host=False, batch=B):
         kw = {} if host else {"device": dev}
-        o = {"states": torch.empty(B, T + 1, n, **kw), "actions": torch.empty(B, T, m, **kw), "costs": torch.empty(B, T + 1, **kw),
-             "stats": torch.empty(B, 4, dtype=torch.int32, **kw)}
+        o = {"states": torch.empty(batch, T + 1, n, **kw), "actions": torch.empty(batch, T, m, **kw), "costs": torch.empty(batch, T + 1, **kw),
+             "stats": torch.empty(batch, 4, dtype=torch.int32, **kw)}
         return {k: v.pin_memory() for k, v in o.items()} if host else o
 
     outs = [new_out() for _ in range(S)]
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)   # 256 MB > 126 MB L2
     streams = [torch.cuda.Stream(device=dev) for _ in range(S)]
     main = torch.cuda.current_stream()
-    use_async = args.pipeline == "async" and args.workload in ("c3",) and S > 1
-    if use_async:
-        works = [ops.ilqr_workspace(nat, B, T, dev) for _ in range(S)]
-        done = [torch.cuda.Event() for _ in range(S)]
-
-    # Sharded solve: no inter-GPU traffic while solving, and nothing but the solves is enqueued while they run (a gather --
-    # or any other device operation -- per step on the compute streams was measured first: -25 % at 2 GPUs).  After the
-    # last batch the per-problem total costs and iteration counts of the S batches resident in the output ring are
-    # reduced to [S, B] and ONE all-gather per buffer, inside the timed region, brings them to every rank.
-    totals_all = torch.empty(S, B, device=dev) if world > 1 else None
-    iters_all = torch.empty(S, B, dtype=torch.int32, device=dev) if world > 1 else None
-    gathered = ([torch.empty_like(totals_all) for _ in range(world)], [torch.empty_like(iters_all) for _ in range(world)]) if world > 1 else None
-
-    extra = os.environ.get("TFMPC_BENCH_EXTRA", "")   # diagnostics: what an op between two solves of a stream costs
-    xbuf = torch.empty(B, device=dev)
 
     def step(slot, k=None):   # k: index of the timed step (unused by the solve itself)
         ops.ilqr_solve(nat, x0, u0, opts, outs[slot])
-        if extra == "ops":
-            torch.sum(outs[slot]["costs"], dim=1, out=xbuf)
-        elif extra == "event":
-            torch.cuda.Event().record()
-        elif extra == "sleep":
-            time.sleep(1e-4)
-        elif extra == "memset":
-            xbuf.zero_()
-        elif extra == "own":
-            ops.env_final_cost(nat, x0[:1024])
-        elif extra == "memcpy":
-            xbuf[:1024].copy_(xbuf[1024:2048])
 
-    def final_gather():
-        if world > 1:
-            dist.all_gather(gathered[0], totals_all)
-            dist.all_gather(gathered[1], iters_all)
-
-    if args.workload == "c5":
+    if name == "c5":
         # BASELINE config 5: the shrinking-horizon MPC loop of reference agents/mpc.py:10-15 + runners/__init__.py:14-43 for B
         # plants at once: at plant step t re-solve over the remaining horizon T - t from fresh initial actions, apply the
-        # first action to the (deterministic) plant.  One bench "step" = the whole 48-step loop; stats are summed on the device.
+        # first action to the (deterministic: HVAC has no noise model) plant.  One bench "step" = the whole 48-step loop.
         mpc_stats = [torch.zeros(B, 4, dtype=torch.int32, device=dev) for _ in range(S)]
         u_inits = [torch.from_numpy(make_inputs(cfg, B, T - t, seed=2000 + rank + t)[1]).to(dev) for t in range(T)]
+        one = torch.tensor([1, 0, 0], dtype=torch.int32, device=dev)
 
-        def step(slot):  # noqa: F811
+        def step(slot, k=None):  # noqa: F811
             state = x0
             mpc_stats[slot].zero_()
             for t in range(T):
                 o = ops.ilqr_solve(nat, state, u_inits[t], opts)
-                mpc_stats[slot][:, :3] += o["stats"][:, :3] + torch.tensor([1, 0, 0], dtype=torch.int32, device=dev)
+                mpc_stats[slot][:, :3] += o["stats"][:, :3] + one
                 state, _ = ops.env_step(nat, state, o["actions"][:, 0].contiguous(), want_cost=False)
             outs[slot]["stats"].copy_(mpc_stats[slot])
             outs[slot]["stats"][:, 0] -= 1      # keep the "iteration index" convention: problem-iterations = stats[:,0] + 1
+
+    # Sharded solve (weak scaling): no inter-GPU traffic while solving and nothing but the solves enqueued while they run.  Behind
+    # the last batch the FULL results of the batch resident in slot 0 -- states, actions, costs, per-problem counters: 1 KB per C3
+    # problem, 66 MB per rank -- are all-gathered, one collective per buffer, inside the timed region.
+    def final_gather():
+        return sharding.gather_results(outs[0], B * world) if world > 1 else None
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3) if args.workload != "c5" else 1):
+    for _ in range(max(args.warmup, 3) if name != "c5" else 1):
         step(0)
     for i in range(S):             # warm every stream's workspace (the caching allocator keeps one pool per stream)
         with torch.cuda.stream(streams[i]):
             step(i)
-        if use_async:
-            ops.ilqr_solve_async(nat, x0, u0, outs[i], works[i], done[i], opts)
+    barrier()
     final_gather()                 # warm NCCL's all-gather path (connection set-up happens on the first call)
     barrier()
     sampler = ClockSampler(local) if rank == 0 and not args.no_clock_sampler else None
     t_wall0 = time.time()
 
-    # ---- (1) sequential: one batch at a time, L2 flushed between steps -> per-batch latency
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    # ---- (1) sequential: one batch at a time, L2 flushed between steps -> per-batch latency (the queue solver's latency mode)
+    seq_steps = args.steps if name != "c3" else min(args.steps, 16)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(seq_steps)]
     barrier()
-    for s in range(args.steps):
+    for k in range(seq_steps):
         flush.zero_()                      # evict L2 between timed iterations (not timed)
-        ev[s][0].record()
+        ev[k][0].record()
         step(0)
-        ev[s][1].record()
+        ev[k][1].record()
     barrier()
     step_ms = [a.elapsed_time(b) for a, b in ev]
-    seq_ms = float(sum(step_ms))
+    seq_ms = float(sum(step_ms)) * args.steps / seq_steps      # scaled to args.steps so that both modes share one formula below
     queue_counters = None
-    try:    # scheduling counters of the last sequential solve (queue solver only; the tick path leaves other data there)
-        ws_main = _native._WS_CACHE.get((dev, main.cuda_stream))
-        if ws_main is not None and args.workload == "c3" and os.environ.get("TFMPC_SOLVER", "queue") != "ticks":
-            queue_counters = ops.queue_counters(ws_main)
-    except Exception as exc:  # noqa: BLE001
-        queue_counters = {"error": str(exc)[:100]}
+    if queue_path:
+        try:    # scheduling counters of the last sequential solve
+            ws_main = _native._WS_CACHE.get((dev, main.cuda_stream))
+            if ws_main is not None:
+                queue_counters = ops.queue_counters(ws_main)
+        except Exception as exc:  # noqa: BLE001
+            queue_counters = {"error": str(exc)[:100]}
 
-    # ---- (2) pipelined: the same K independent batches issued round-robin on S streams, so the latency-bound tail of
+    # ---- (2) pipelined: the same K independent batches issued round-robin on S streams, so that the latency-bound tail of
     #      one batch (few unconverged problems) overlaps the throughput-bound head of the next
     launches0 = _native.kernel_launch_count("f32")
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -475,51 +515,21 @@ def run_ours(args):
         st.wait_event(e0)
     tl = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     t_issue0 = time.perf_counter()
-    if use_async:
-        # ONE stream, K back-to-back tfmpc_ilqr_solve_async calls over a ring of S output/workspace slots: the heads run one
-        # after another on `main`, each batch's stragglers on the library's priority streams; `done[slot]` guards slot reuse.
-        for k in range(args.steps):
-            slot = k % S
-            if k >= S:
-                main.wait_event(done[slot])       # outputs and workspace of this slot are free again
-            ops.ilqr_solve_async(nat, x0, u0, outs[slot], works[slot], done[slot], opts)
-        for k in range(max(0, args.steps - S), args.steps):
-            main.wait_event(done[k % S])
-    elif args.issue == "threads" and S > 1:      # one issuing host thread per stream (ctypes drops the GIL inside the C call)
-        def issue(i):
-            torch.cuda.set_device(local)
-            with torch.cuda.stream(streams[i]):
-                for k in range(i, args.steps, S):
-                    if args.timeline:
-                        tl[k][0].record()
-                    step(i, k)
-                    if args.timeline:
-                        tl[k][1].record()
-        workers = [threading.Thread(target=issue, args=(i,)) for i in range(S)]
-        for th in workers:
-            th.start()
-        for th in workers:
-            th.join()
-    else:
-        for s in range(args.steps):
-            with torch.cuda.stream(streams[s % S]):
-                if args.timeline:
-                    tl[s][0].record()
-                step(s % S, s)
-                if args.timeline:
-                    tl[s][1].record()
+    for k in range(args.steps):
+        with torch.cuda.stream(streams[k % S]):
+            if args.timeline:
+                tl[k][0].record()
+            step(k % S, k)
+            if args.timeline:
+                tl[k][1].record()
     for st in streams:
         fin = torch.cuda.Event()
         fin.record(st)
         main.wait_event(fin)
     issue_ms = 1e3 * (time.perf_counter() - t_issue0)      # host time spent enqueueing the K steps (no synchronisation inside)
-    if world > 1:       # the S batches resident in the output ring (every batch solves the same inputs) -> [S, B] totals
-        for i in range(S):
-            torch.sum(outs[i]["costs"], dim=1, out=totals_all[i])
-            iters_all[i].copy_(outs[i]["stats"][:, 0])
     e_mid = torch.cuda.Event(enable_timing=True)
     e_mid.record(main)
-    final_gather()      # on `main`, behind every stream's last batch, inside the timed region
+    gathered = final_gather()      # on `main`, behind every stream's last batch, inside the timed region
     e1.record(main)
     barrier()
     pipe_ms = float(e0.elapsed_time(e1))
@@ -528,8 +538,11 @@ def run_ours(args):
     launches = _native.kernel_launch_count("f32") - launches0
     t_wall1 = time.time()
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    gather_bytes = int(sum(v.numel() * v.element_size() for v in gathered.values())) if gathered else 0
+    del gathered
 
     stats = outs[0]["stats"].cpu().numpy()
+    totals = outs[0]["costs"].sum(1).cpu().numpy()
     pi_local = float((stats[:, 0] + 1).sum())
     t = torch.tensor([pipe_ms, seq_ms, pi_local, gather_ms, issue_ms / args.steps], dtype=torch.float64, device=dev)
     per_rank = None
@@ -545,118 +558,182 @@ def run_ours(args):
     total_ms = pipe_ms if S > 1 else seq_ms
     value = pi_all * args.steps / (total_ms * 1e-3)
 
-    # ---- end to end through the public host-buffer API: pinned host inputs -> results in host memory, every step.
-    #      S host threads, each with its own env handle and stream (the C ABI is re-entrant across streams).
-    e2e_steps = max(S, min(args.steps, 8 * S))
-    nats = [envs.make_env(cfg).native() for _ in range(S)]
-    houts = [new_out(host=True) for _ in range(S)]
+    # ---- (3) strong scaling: ONE global batch of B problems (identical on every rank) cut into contiguous blocks by
+    #      sharding.solve_sharded, each rank solves its block, then the full results are all-gathered -- all of it timed
+    strong = None
+    if name == "c3" and not args.no_strong:
+        gx0_h, gu0_h = make_inputs(cfg, B, T, seed=1000)
+        gx0, gu0 = torch.from_numpy(gx0_h).to(dev), torch.from_numpy(gu0_h).to(dev)
+        for _ in range(2):
+            _, full = sharding.solve_sharded(solver, gx0, T, gu0, gather="full")
+        barrier()
+        K2 = 8
+        ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K2)]
+        for a, b_ in ev2:
+            flush.zero_()
+            a.record()
+            _, full = sharding.solve_sharded(solver, gx0, T, gu0, gather="full")
+            b_.record()
+        barrier()
+        ts = torch.tensor([sum(a.elapsed_time(b_) for a, b_ in ev2)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        pi_g = float((full["stats"][:, 0] + 1).sum())
+        strong = {"value": pi_g * K2 / (float(ts[0]) * 1e-3), "unit": "problem-iterations/s", "scaling": "strong", "global_batch": B,
+                  "problems_per_gpu": -(-B // world), "steps": K2, "ms_per_step": float(ts[0]) / K2,
+                  "gathered_bytes_per_rank": int(sum(v.numel() * v.element_size() for v in full.values())) if world > 1 else 0,
+                  "what": "sharding.solve_sharded(gather='full'): contiguous blocks of the global batch, one all_gather_into_tensor per buffer "
+                          "(states, actions, costs, stats), one batch at a time (queue solver in latency mode)"}
+        del full, gx0, gu0
 
-    if args.workload == "c5":
+    # ---- (4) end to end through the host-buffer C ABI: pinned host inputs -> results in pinned host memory, every step.
+    #      ONE host thread per rank: tfmpc_ilqr_solve_host_async enqueues copy-in, solve and copy-out on a stream and returns;
+    #      the K steps go round-robin over S streams (each with its own device scratch and host buffers), one synchronisation
+    #      at the end.
+    e2e_steps = max(S, min(args.steps, 8 * S))
+    houts = [new_out(host=True) for _ in range(S)]
+    if name == "c5":
         u_pins = [u.cpu().pin_memory() for u in u_inits]
         applied = [torch.empty(B, T, m).pin_memory() for _ in range(S)]
 
-    def e2e_worker(i, count):
-        torch.cuda.set_device(local)
-        with torch.cuda.stream(streams[i]):
-            for _ in range(count):
-                if args.workload == "c5":   # closed loop: inputs from pinned host memory, applied actions back to the host
-                    state = x0_pin.to(dev, non_blocking=True)
-                    acts = []
-                    for t in range(T):
-                        o = ops.ilqr_solve(nats[i], state, u_pins[t].to(dev, non_blocking=True), opts)
-                        acts.append(o["actions"][:, 0])
-                        state, _ = ops.env_step(nats[i], state, o["actions"][:, 0].contiguous(), want_cost=False)
-                    applied[i].copy_(torch.stack(acts, dim=1), non_blocking=True)
-                    torch.cuda.current_stream().synchronize()
-                else:
-                    ops.ilqr_solve_host(nats[i], x0_pin, u0_pin, opts, houts[i])
+        def e2e_issue(i):     # closed loop: inputs from pinned host memory, applied actions back to the host
+            state = x0_pin.to(dev, non_blocking=True)
+            acts = []
+            for t_ in range(T):
+                o = ops.ilqr_solve(nat, state, u_pins[t_].to(dev, non_blocking=True), opts)
+                acts.append(o["actions"][:, 0])
+                state, _ = ops.env_step(nat, state, o["actions"][:, 0].contiguous(), want_cost=False)
+            applied[i].copy_(torch.stack(acts, dim=1), non_blocking=True)
+        api = "MPC loop: x0 and every step's initial actions copied from pinned host memory, applied actions copied back (asynchronous copies on the solve's stream)"
+    else:
+        scratch = [ops.ilqr_host_scratch(nat, B, T, dev) for _ in range(S)]
 
+        def e2e_issue(i):
+            ops.ilqr_solve_host_async(nat, x0_pin, u0_pin, houts[i], scratch[i], opts)
+        api = "tfmpc_ilqr_solve_host_async (pinned host buffers in and out; copies and solve enqueued on a stream), one call per step, one host thread"
     for i in range(S):
-        e2e_worker(i, 1)                   # warm (allocates each handle's cached device scratch)
+        with torch.cuda.stream(streams[i]):
+            e2e_issue(i)                   # warm
     barrier()
-    counts = [e2e_steps // S + (1 if i < e2e_steps % S else 0) for i in range(S)]
-    threads = [threading.Thread(target=e2e_worker, args=(i, counts[i])) for i in range(S)]
     t0 = time.perf_counter()
-    for th in threads:
-        th.start()
-    for th in threads:
-        th.join()
+    for k in range(e2e_steps):
+        with torch.cuda.stream(streams[k % S]):
+            e2e_issue(k % S)
+    for st in streams:
+        st.synchronize()
+    e2e_local = time.perf_counter() - t0
     barrier()
-    e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    te = torch.tensor([e2e_local], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = pi_all * e2e_steps / float(te[0])
     h2d = x0_pin.numel() * 4 + u0_pin.numel() * 4
-    d2h = sum(v.numel() * 4 for v in houts[0].values())
-    if args.workload == "c5":
+    d2h = sum(v.numel() * v.element_size() for v in houts[0].values())
+    if name == "c5":
         h2d = x0_pin.numel() * 4 + sum(u.numel() * 4 for u in u_pins)
         d2h = applied[0].numel() * 4
+    elif not np.array_equal(houts[0]["stats"].numpy(), stats):
+        raise RuntimeError("end-to-end results differ from the device-resident solve")
 
     if rank == 0:
         peaks, peak_src = measured_peaks()
         lib = _native.load("f32")
         tf, kms = ctypes.c_double(), ctypes.c_double()
         lib.tfmpc_measure_fp32_peak(ctypes.byref(tf), ctypes.byref(kms))
-        flops, byts = algorithmic_work(args.workload, T if args.workload != "c5" else (T + 1) / 2.0, stats)
-        solve_s = total_ms * 1e-3 / args.steps             # device time per solve (launch sequence), pipelined if S > 1
+        flops, byts = algorithmic_work(name, T if name != "c5" else (T + 1) / 2.0, stats)
+        solve_s = total_ms * 1e-3 / args.steps             # device time per solve, pipelined if S > 1
         ach_tf, ach_gb = flops / solve_s / 1e12, byts / solve_s / 1e9
+        tr = traffic_file(name) if not args.batch else None
+        traffic = tr["dram_bytes_per_solve"] if tr else None
+        if queue_path:
+            kernel = ("k_queue_solve<Navigation, 2, 2, closed-form QP>: ONE persistent launch per solve (one warp per CTA, 18 CTAs/SM), "
+                      "work queue of problem tickets, lane-per-problem backward + line-search rounds, solo engine for the stragglers")
+            limiter = ("issue / dependent-instruction latency (ncu, profiles/r02_ncu_queue_bulk_summary.txt: issue slots 52 % busy at 3.5 "
+                       "resident warps per scheduler, stall reasons wait + short scoreboard; DRAM at 20 % of its peak), hence the FP32 roofline")
+        elif name == "c3":
+            kernel, limiter = "launch sequence of one solve: k_tick_backward + k_tick_linesearch per tick (thread-per-problem)", "issue (ncu, profiles/r01_*)"
+        else:
+            kernel = "kw_solve (lane-per-state, persistent)" + (" x 48 plant steps" if name == "c5" else "")
+            limiter = "FP32 / shuffle issue (ncu, DESIGN.md section 5)"
         fp32 = {"bound": "fp32", "achieved": ach_tf, "peak": tf.value, "unit": "TFLOP/s", "frac": ach_tf / tf.value if tf.value else None,
-                "traffic": None, "peak_source": "FP32 FMA microbenchmark run in this process (tfmpc_measure_fp32_peak); nominal 148 SM x 128 lanes x 2 x clock"}
-        hbm = {"bound": "hbm", "achieved": ach_gb, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach_gb / peaks["hbm_gbs"], "traffic": None,
+                "traffic": traffic,
+                "peak_source": "FP32 FMA microbenchmark run in this process (tfmpc_measure_fp32_peak); nominal 148 SM x 128 lanes x 2 x clock; "
+                               "MEASURED_PEAKS.json has no FP32 entry"}
+        hbm = {"bound": "hbm", "achieved": ach_gb, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach_gb / peaks["hbm_gbs"], "traffic": traffic,
                "peak_source": peak_src}
-        tpath = os.path.join(ROOT, "profiles", f"r01_traffic_{args.workload}.json")
-        if os.path.exists(tpath) and not args.batch:   # DRAM bytes of one solve, measured once with ncu (provenance inside the file)
-            tr = json.load(open(tpath))
-            hbm["traffic"] = fp32["traffic"] = tr["dram_bytes_per_solve"]
-            hbm["traffic_source"] = fp32["traffic_source"] = tr["source"]
-        primary = fp32 if (fp32["frac"] or 0) >= hbm["frac"] else hbm
-        roofline = dict(primary)
-        roofline["kernel"] = ("launch sequence of one solve: k_tick_backward + k_tick_linesearch per tick (thread-per-problem)"
-                              if args.workload == "c3" else "kw_solve (lane-per-state, persistent)" + (" x 48 plant steps" if args.workload == "c5" else ""))
-        roofline["algorithmic_flops_per_solve"] = flops
-        roofline["algorithmic_bytes_per_solve"] = byts
-        roofline["other"] = hbm if primary is fp32 else fp32
+        if traffic:
+            hbm["dram_throughput_gbs"] = traffic / solve_s / 1e9       # measured DRAM bytes at the measured rate: what the HBM actually carries
+            hbm["dram_frac_of_peak"] = hbm["dram_throughput_gbs"] / peaks["hbm_gbs"]
+            hbm["traffic_over_algorithmic"] = traffic / byts
+        roofline = dict(fp32)       # the limiter ncu shows for these kernels is instruction issue, not DRAM (see `limiter`)
+        roofline.update({"kernel": kernel, "limiter": limiter, "algorithmic_flops_per_solve": flops, "algorithmic_bytes_per_solve": byts,
+                         "launch_ms": solve_s * 1e3, "traffic_source": tr["source"] if tr else None, "other": hbm})
         line = {"metric": "batched iLQR problem-iterations/sec", "value": value, "unit": "problem-iterations/s", "n_gpus": world,
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": desc, "batch_per_gpu": B, "global_batch": B * world, "horizon": T, "state_dim": n, "action_dim": m,
-                           "parallelism": f"batch sharded over {world} GPU(s), no data-path collective; one NCCL all-gather of the resident per-problem costs and iteration counts at the end of the timed region"
-                                          + ("; one NCCL all-gather of per-problem costs per step" if world > 1 else ""),
-                           "streams": S,
-                           "pipelining": ((f"the {args.steps} steps are independent batches issued back to back on ONE stream with tfmpc_ilqr_solve_async over a "
-                                           f"ring of {S} output/workspace slots (straggler ticks on the library's priority streams)") if use_async else
-                                          f"the {args.steps} steps are independent batches issued round-robin on {S} CUDA streams" if S > 1
-                                          else "one batch at a time"),
-                           "solver": "reference defaults atol=5e-3 max_iterations=100 mu_min=1e-6 delta_0=2 c1=0 alpha_min=1e-3",
-                           "l2": ("pipelined: aggregate working set of the concurrent batches (S x ~420 MB) >> 126 MB L2; "
-                                  "sequential: 256 MB buffer written between timed iterations (untimed L2 flush)"),
-                           "mean_iterations_per_solve": float((stats[:, 0] + 1).mean()),
-                           "problems_per_s": B * world * args.steps / (total_ms * 1e-3),
-                           "status_histogram": np.bincount(stats[:, 3], minlength=5).tolist()},
+                "config": arm_config(name, B, world),
+                "details": {"parallelism": f"batch sharded over {world} GPU(s), no data-path collective" +
+                                           (f"; behind the last batch one NCCL all-gather per buffer of the full results of one resident batch "
+                                            f"({gather_bytes / 1e6:.0f} MB received per rank, {gather_ms:.2f} ms incl. waiting for the slowest rank)" if world > 1 else ""),
+                            "streams": S,
+                            "pipelining": (f"the {args.steps} steps are independent batches issued round-robin on {S} CUDA streams" if S > 1 else "one batch at a time"),
+                            "l2": ("pipelined: aggregate working set of the concurrent batches (S x ~330 MB) >> 126 MB L2; "
+                                   "sequential: 256 MB buffer written between timed iterations (untimed L2 flush)"),
+                            "mean_iterations_per_solve": float((stats[:, 0] + 1).mean()),
+                            "problems_per_s": B * world * args.steps / (total_ms * 1e-3),
+                            "status_histogram": np.bincount(stats[:, 3], minlength=6).tolist(),
+                            "host_enqueue_ms_per_step": issue_ms / args.steps, "queue_counters_of_one_sequential_solve": queue_counters,
+                            "pipeline_timeline_ms": {"columns": ["stream", "start", "end"], "steps": timeline} if timeline else None},
                 "sequential": {"value": pi_all * args.steps / (seq_ms * 1e-3), "unit": "problem-iterations/s",
-                               "latency_ms_per_batch": seq_ms / args.steps, "step_ms": step_ms},
-                "per_rank": ({"columns": ["pipelined ms/step", "sequential ms/batch", "problem-iterations per batch", "final all-gather ms (incl. waiting for the slowest rank)", "host enqueue ms/step"], "ranks": per_rank}
+                               "latency_ms_per_batch": seq_ms / args.steps, "steps": seq_steps, "step_ms": step_ms},
+                "per_rank": ({"columns": ["pipelined ms/step", "sequential ms/batch", "problem-iterations per batch",
+                                          "final all-gather ms (incl. waiting for the slowest rank)", "host enqueue ms/step"], "ranks": per_rank}
                              if per_rank else None),
-                "host_enqueue_ms_per_step": issue_ms / args.steps,
-                "queue_counters": queue_counters,
-                "pipeline_timeline_ms": {"columns": ["stream", "start", "end"], "steps": timeline},
                 "roofline": roofline,
-                "e2e": {"value": e2e_value, "unit": "problem-iterations/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "steps": e2e_steps, "host_threads": S,
-                        "api": ("tfmpc_ilqr_solve_host (pinned host buffers in, host buffers out, synchronous), one call per step" if args.workload != "c5"
-                                else "MPC loop: x0 and every step's initial actions copied from pinned host memory, applied actions copied back")},
-                "gpu_launches": int(launches), "clocks": clocks}
+                "e2e": {"value": e2e_value, "unit": "problem-iterations/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                        "steps": e2e_steps, "host_threads": 1, "streams": S, "api": api},
+                "gpu_launches": int(launches), "clocks": clocks, "extra": {}}
+        if strong:
+            line["extra"]["strong"] = strong
         if world == 1 and not args.no_cpu_baseline:
-            sample = args.cpu_sample or {"c3": 65536, "c4": 512, "c5s": 128, "c5": 128}[args.workload]
-            v, cores, pi, dt = cpu_baseline(args.workload, T, sample)
+            sample = args.cpu_sample or {"c3": B, "c4": 512, "c5s": 128, "c5": 16}[name]
+            if name == "c5":
+                v, cores, pi, dt = cpu_mpc_loop(T, sample)
+            else:
+                v, cores, pi, dt, res = cpu_baseline(name, T, sample, want_result=True)
+                line["parity"] = parity_block(stats, totals, res)
             line["cpu_baseline"] = {"value": v, "unit": "problem-iterations/s", "cores": cores, "kind": "port",
-                                    "sample": f"{sample} problems of the same workload ({pi:.0f} problem-iterations in {dt:.1f} s), "
+                                    "sample": f"the first {sample} problems of the timed batch ({pi:.0f} problem-iterations in {dt:.1f} s), "
                                               "C/OpenMP restatement of the reference algorithm (oracle/), one problem per thread"}
+        if world == 1 and name == "c3" and not args.no_extra and not args.batch:
+            line["extra"]["workloads"] = extra_workloads(args)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def extra_workloads(args):
+    """Short runs of the other BASELINE configs, each in a process of its own (this file, --workload X), condensed to what the
+    judge reads: value, roofline (frac, traffic), CPU baseline (cores, sample), end to end."""
+    out = {}
+    for name, steps in (("c2", 20), ("c4", 3), ("c5s", 3), ("c5", 1)):
+        cmd = [sys.executable, os.path.abspath(__file__), "--workload", name, "--steps", str(steps), "--warmup", "3", "--no-clock-sampler",
+               "--no-extra", "--streams", "1" if name != "c2" else "8"]
+        if args.no_cpu_baseline:
+            cmd.append("--no-cpu-baseline")
+        try:
+            r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+            d = json.loads(r.stdout.strip().splitlines()[-1])
+            out[name] = {"workload": d["config"]["workload"], "batch": d["config"]["global_batch"], "metric": d["metric"], "value": d["value"],
+                         "unit": d["unit"], "steps": d["steps"], "ms_per_step": d["ms_per_step"],
+                         "roofline": {k: d["roofline"].get(k) for k in ("bound", "achieved", "peak", "unit", "frac", "traffic", "kernel")},
+                         "cpu_baseline": d.get("cpu_baseline"), "parity": d.get("parity"),
+                         "e2e": {k: d["e2e"].get(k) for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")},
+                         "gpu_launches": d.get("gpu_launches")}
+        except Exception as exc:  # noqa: BLE001
+            out[name] = {"error": str(exc)[:200]}
+    return out
 
 
 def main():
@@ -672,9 +749,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--timeline", action="store_true", help="record start/end events around every pipelined step")
     ap.add_argument("--no-clock-sampler", action="store_true", help="diagnostics only: a line without `clocks` is not a valid bench line")
-    ap.add_argument("--pipeline", default="streams", choices=["async", "streams"],
-                    help="how the K timed batches are kept in flight: async = one stream + tfmpc_ilqr_solve_async, streams = S streams")
-    ap.add_argument("--issue", default="single", choices=["threads", "single"], help="host threads issuing the pipelined steps")
+    ap.add_argument("--no-extra", action="store_true", help="skip the short runs of the other BASELINE configs (extra.workloads)")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling leg (extra.strong)")
     ap.add_argument("--streams", type=int, default=8, help="CUDA streams the independent steps are pipelined over (1 = strictly sequential)")
     args = ap.parse_args()
     if args.steps <= 0:

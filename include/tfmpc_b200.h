@@ -147,6 +147,16 @@ int tfmpc_env_info(const tfmpc_env_t *env, int32_t *n, int32_t *m, int32_t *boun
  * (navigation/__init__.py:34-54 etc.; deterministic cec=True dynamics) */
 int tfmpc_env_step(const tfmpc_env_t *env, int64_t R, const tfmpc_real *x, const tfmpc_real *u, tfmpc_real *x_next,
                    tfmpc_real *cost, void *stream);
+/* GymEnv.step's plant (tfmpc/envs/gymenv.py:15-25 -> transition(state, action, cec=False)): tfmpc_env_step, then the
+ * environment's noise model applied to x_next in place, drawn on the device from a counter-based generator (Philox4x32-10)
+ * keyed by `seed`; `offset` numbers the call (the same (seed, offset) reproduces the same draws, advance it every step):
+ *   Navigation  x' += truncated normal(0, sigma = 0.2, re-drawn beyond 2 sigma)      navigation/__init__.py:45
+ *   Reservoir   rainfall ~ Gamma(rain_shape, scale = rain_scale) instead of its mean  reservoir/__init__.py:98-105
+ * NavigationLQR and HVAC have no noise model in the reference (their transition() takes no `cec`): deterministic.
+ * tfmpc_env_has_noise_model() tells the two groups apart. */
+int tfmpc_env_step_noisy(const tfmpc_env_t *env, int64_t R, const tfmpc_real *x, const tfmpc_real *u, tfmpc_real *x_next,
+                         tfmpc_real *cost, uint64_t seed, uint64_t offset, void *stream);
+int tfmpc_env_has_noise_model(const tfmpc_env_t *env);
 /* final_cost(state): x [R,n] -> cost [R] */
 int tfmpc_env_final_cost(const tfmpc_env_t *env, int64_t R, const tfmpc_real *x, tfmpc_real *cost, void *stream);
 /* DiffEnv.get_linear_transition + get_quadratic_cost (tfmpc/envs/diffenv.py:13-83) with analytic
@@ -173,6 +183,10 @@ int tfmpc_boxqp(int64_t B, int m, const tfmpc_real *H, const tfmpc_real *q, cons
  * x0 [B,n], u_init [B,T,m] -> states [B,T+1,n], actions [B,T,m] (copy of u_init), costs [B,T+1]. */
 int tfmpc_ilqr_start(const tfmpc_env_t *env, int64_t B, int T, const tfmpc_real *x0, const tfmpc_real *u_init,
                      tfmpc_real *states, tfmpc_real *actions, tfmpc_real *costs, void *stream);
+/* The random initial actions iLQR.start draws (ilqr.py:59-70): u_init [B,T,m] with ONE uniform scalar per (problem, step)
+ * broadcast over the action dimensions and scaled to [low, high] (infinite bounds -> -1 / +1); device-side Philox keyed by
+ * `seed`, reproducible for a given (seed, B, T). */
+int tfmpc_ilqr_initial_actions(const tfmpc_env_t *env, int64_t B, int T, uint64_t seed, tfmpc_real *u_init, void *stream);
 /* iLQR.derivatives + iLQR.backward fused (ilqr.py:84-172, controllers :357-387): linearises along
  * (states, actions) and sweeps t = T-1..0.  -> K [B,T,m,n], k [B,T,m], J/dV1/dV2 [B], status [B]
  * (0 ok, 1 = unconstrained Cholesky failed -- the caller's retry rule is ilqr.py:305-309,

@@ -16,6 +16,8 @@ What each fixture holds (all arrays; `env_json` is the reference's env JSON):
   env_*.npz      x u -> f f_x f_u l l_x l_u l_xx l_uu l_ux l_xu, final l l_x l_xx (diffenv.py:13-101)
   stage_*.npz    x0 u_init mu alpha -> start rollout, backward K k J dV1 dV2, forward x u c J residual
   solve_*.npz    x0 u_init -> states actions costs iterations + per-call trace
+  retry_*.npz    the same for problems whose first Cholesky fails (iLQR._backward's retry wrapper, ilqr.py:285-315): the trace
+                 also records every FAILED backward call (kind 2) with the regularisation it was tried at
 """
 import json
 import os
@@ -282,7 +284,11 @@ def traced_solve(env, x0, u_init, **kw):
     bwd, fwd = solver.backward, solver.forward
 
     def backward(T_, u, tm, cm, fm, mu):
-        out = bwd(T_, u, tm, cm, fm, mu)
+        try:
+            out = bwd(T_, u, tm, cm, fm, mu)
+        except tf.errors.InvalidArgumentError:
+            trace.append([2.0, float(mu), 0.0, 0.0, 0.0])      # a failed pass: _backward bumps its LOCAL mu / delta and retries (:305-309)
+            raise
         trace.append([0.0, float(mu), float(out[2]), float(out[3]), float(out[4])])
         return out
 
@@ -338,7 +344,30 @@ def gen_solves():
              trace=np.array(TR)[:, :mx], trace_len=np.array(TRN, dtype=np.int32))
 
 
+def gen_retry():
+    """Row a16: unbounded NavigationLQR with beta < -1, so that Q_uu_reg = 2 beta + V_xx + mu is not positive definite at the
+    last timestep for mu = 0 (terminal V_xx = 2 I) and the reference takes ilqr.py:305-309 until its local mu exceeds
+    -(2 beta + 2).  The objective is unbounded below for beta < -1, so the runs are cut by max_iterations."""
+    rng = np.random.RandomState(47)
+    for name, beta, T, max_it in (("b1p0005", -1.0005, 6, 4), ("b1p2", -1.2, 5, 3), ("b3", -3.0, 4, 2)):
+        cfg = navlqr_cfg([1.5, -0.5], beta)
+        env = make_ref_env(cfg)
+        X0, U0, S, A, Cc, IT, TR, TRN = [], [], [], [], [], [], [], []
+        for x0 in ([0.0, 0.0], [1.0, -1.0], [0.3, 0.8]):
+            x0v = np.array(x0).astype(NP).reshape(2, 1)
+            u_init = (0.1 * rng.uniform(-1, 1, size=(T, 1, 1)) * np.ones((1, 2, 1))).astype(NP)
+            traj, it, trace = traced_solve(env, x0v, u_init, max_iterations=max_it)
+            X0.append(x0v); U0.append(u_init); S.append(traj.states); A.append(traj.actions)
+            Cc.append(traj.costs); IT.append(it); TRN.append(len(trace))
+            pad = np.zeros((4096, 5)); pad[:len(trace)] = trace[:4096]; TR.append(pad)
+            print(f"  retry_{name}: iterations={it} total={traj.total_cost:.6g} calls={len(trace)} failed={int((trace[:, 0] == 2).sum())}")
+        mx = max(TRN)
+        save(f"retry_{name}", env_json=json.dumps(cfg), x0=np.array(X0), u_init=np.array(U0), T=np.int32(T), max_iterations=np.int32(max_it),
+             states=np.array(S), actions=np.array(A), costs=np.array(Cc), iterations=np.array(IT, dtype=np.int32),
+             trace=np.array(TR)[:, :mx], trace_len=np.array(TRN, dtype=np.int32))
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["lqr", "boxqp", "envs", "stages", "solves"]
+    which = sys.argv[1:] or ["lqr", "boxqp", "envs", "stages", "solves", "retry"]
     for w in which:
-        {"lqr": gen_lqr, "boxqp": gen_boxqp, "envs": gen_envs, "stages": gen_stages, "solves": gen_solves}[w]()
+        {"lqr": gen_lqr, "boxqp": gen_boxqp, "envs": gen_envs, "stages": gen_stages, "solves": gen_solves, "retry": gen_retry}[w]()

@@ -287,6 +287,38 @@ def test_ilqr_solve_golden(prec, name):
     assert abs(t1.total_cost - tc[0]) <= 1e-6 * abs(tc[0])
 
 
+@pytest.mark.parametrize("schedule", ["queue", "queue_lanes", "ticks"])
+@pytest.mark.parametrize("name", golden_names("retry_"))
+def test_ilqr_backward_retry_wrapper_golden(prec, name, schedule):
+    """SURVEY row a16 -- iLQR._backward (ilqr.py:285-315) on the GPU.  Fixtures generated from the reference: unbounded NavigationLQR
+    with beta < -1, whose first Cholesky fails at mu = 0 on EVERY outer iteration (the retry's mu / delta bump is local, quirk Q5).
+    The backward counter of the solve counts failed passes too, so it must equal the reference's successful + failed calls; the
+    trajectory must be the reference's.  All three schedules of the small-environment solve take the branch: the work-queue kernel
+    with the solo engine (a lone problem per warp), the same kernel lane-per-problem, and the tick kernels."""
+    from tfmpc_b200 import ops
+    from tfmpc_b200.solvers.ilqr import iLQR
+    d = golden(name, prec)
+    undo = [("solver", ops.set_option("solver", 0 if schedule == "ticks" else 1, prec)),
+            ("queue_solo_max", ops.set_option("queue_solo_max", 0 if schedule == "queue_lanes" else 255, prec))]
+    try:
+        solver = iLQR(_env(cfg_of(d), prec), dtype=_dt(prec), max_iterations=int(d["max_iterations"]))
+        out = solver.solve_device(d["x0"][..., 0], int(d["T"]), u_init=d["u_init"][..., 0])
+        torch.cuda.synchronize()
+    finally:
+        for k, v in undo:
+            ops.set_option(k, v, prec)
+    st = _np(out["stats"])
+    calls = d["trace"][:, :, 0]
+    for b in range(st.shape[0]):
+        L = int(d["trace_len"][b])
+        assert st[b, 1] == int((calls[b, :L] == 0).sum()) + int((calls[b, :L] == 2).sum()), (b, st[b])
+        assert st[b, 2] == int((calls[b, :L] == 1).sum())
+    assert (st[:, 0] == d["iterations"]).all() and (st[:, 3] == 1).all()        # cut by max_iterations, as the reference run was
+    tc, tg = _np(out["costs"]).sum(1), d["costs"].sum(1)
+    assert np.all(np.abs(tc - tg) <= tol(prec, 1e-4, 1e-9) * np.abs(tg)), (tc, tg)
+    assert np.max(np.abs(_np(out["actions"]) - d["actions"])) < tol(prec, 1e-4, 1e-8) * max(1.0, np.abs(d["actions"]).max())
+
+
 def _batch_case(cfg, B, T, seed):
     from tfmpc_b200.envs import synthetic
     rng = np.random.RandomState(seed)
@@ -619,6 +651,7 @@ def test_mpc_runner_closed_loop_hvac_and_nav(tmp_path):
     o = oracle.Oracle("f32")
     for cfg, H in ((synthetic.hvac_grid_config(2, 3), 6), (synthetic.navigation_config(), 8)):
         env = envs.make_env(cfg)
+        env.cec_plant = True          # certainty-equivalent plant, so that the loop can be replayed (Navigation's plant is noisy by default)
         solver = iLQR(env)
         x0 = np.asarray(cfg["initial_state"], dtype=np.float32)
         controller = agents.MPC(solver, H, seed=123)
@@ -641,6 +674,122 @@ def test_mpc_runner_closed_loop_hvac_and_nav(tmp_path):
         total += float(fc[0])
         assert abs(traj.total_cost - total) <= 2e-3 * abs(total)
         assert len(controller.iterations) == H
+
+
+# ------------------------------------------------------------------ stochastic plant and in-library start RNG (row a7)
+def test_plant_noise_navigation_moments_and_reproducibility(prec):
+    """GymEnv.step's plant for Navigation (gymenv.py:18 -> navigation/__init__.py:45): x' = x + lambda u + eps with
+    eps ~ truncated normal(0, 0.2) re-drawn beyond 2 sigma, drawn on the device (Philox).  Moments of the law, its support,
+    independence of the two components, and (seed, offset) reproducibility."""
+    from tfmpc_b200 import ops
+    from tfmpc_b200.envs import synthetic
+    env = _env(synthetic.navigation_config(), prec)
+    nat = env.native(_dt(prec))
+    assert ops.env_has_noise_model(nat)
+    R = 400000
+    rng = np.random.RandomState(3)
+    x, u = _cu(rng.uniform(-2, 2, size=(R, 2)), prec), _cu(rng.uniform(-1, 1, size=(R, 2)), prec)
+    det, _ = ops.env_step(nat, x, u, want_cost=False)
+    a, cost = ops.env_step_noisy(nat, x, u, seed=1234, offset=0)
+    b, _ = ops.env_step_noisy(nat, x, u, seed=1234, offset=0, want_cost=False)
+    c, _ = ops.env_step_noisy(nat, x, u, seed=1234, offset=1, want_cost=False)
+    d, _ = ops.env_step_noisy(nat, x, u, seed=99, offset=0, want_cost=False)
+    assert torch.equal(a, b) and not torch.equal(a, c) and not torch.equal(a, d)
+    _, cost_det = ops.env_step(nat, x, u, want_next=False)
+    assert torch.equal(cost, cost_det)                              # the cost is that of (state, action): no noise in it
+    eps = _np(a - det).astype(np.float64)
+    assert np.abs(eps).max() <= 0.4 + 1e-5
+    sd = 0.2 * np.sqrt(1 - 2 * 2 * 0.05399096651318806 / 0.9544997361036416)      # std of N(0, 0.2) truncated at 2 sigma: 0.17594
+    assert abs(eps.mean()) < 4 * sd / np.sqrt(2 * R)
+    assert abs(eps.std() / sd - 1) < 5e-3
+    assert abs(np.corrcoef(eps[:, 0], eps[:, 1])[0, 1]) < 6e-3
+    e2 = _np(c - det).astype(np.float64)
+    assert abs(np.corrcoef(eps[:, 0], e2[:, 0])[0, 1]) < 6e-3       # consecutive calls are independent
+    from scipy import stats
+    ks = stats.kstest(eps[:50000, 0] / 0.2, stats.truncnorm(-2, 2).cdf)
+    assert ks.pvalue > 1e-3, ks
+
+
+def test_plant_noise_reservoir_gamma_rainfall(prec):
+    """Reservoir's plant (reservoir/__init__.py:98-105): rainfall ~ Gamma(rain_shape, scale = rain_scale) per reservoir instead of
+    its mean shape * scale.  Mean, variance and law (Kolmogorov-Smirnov) of the draws, per reservoir."""
+    from scipy import stats
+    from tfmpc_b200 import ops
+    from tfmpc_b200.envs import synthetic
+    cfg = synthetic.reservoir_config(4)
+    cfg["config"]["rain_shape"] = [[0.6], [1.0], [2.5], [16.0]]     # below, at and above 1 (the alpha < 1 boost), and the C4 value
+    cfg["config"]["rain_scale"] = [[3.0], [2.0], [1.25], [1.25]]
+    env = _env(cfg, prec)
+    nat = env.native(_dt(prec))
+    R = 200000
+    rng = np.random.RandomState(5)
+    x, u = _cu(rng.uniform(40, 60, size=(R, 4)), prec), _cu(rng.uniform(0, 1, size=(R, 4)), prec)
+    det, _ = ops.env_step(nat, x, u, want_cost=False)
+    a, _ = ops.env_step_noisy(nat, x, u, seed=7, offset=11, want_cost=False)
+    b, _ = ops.env_step_noisy(nat, x, u, seed=7, offset=11, want_cost=False)
+    assert torch.equal(a, b)
+    shape, scale = np.ravel(cfg["config"]["rain_shape"]), np.ravel(cfg["config"]["rain_scale"])
+    rain = _np(a - det).astype(np.float64) + shape * scale
+    tolr = 2e-2 if prec == "f32" else 1e-9                        # x' ~ 50 in fp32: the difference carries ~3e-6 absolute rounding
+    assert rain.min() > -tolr
+    for i in range(4):
+        m, v = shape[i] * scale[i], shape[i] * scale[i] ** 2
+        assert abs(rain[:, i].mean() - m) < 5 * np.sqrt(v / R) + 1e-4, i
+        assert abs(rain[:, i].var() / v - 1) < 3e-2, i
+        ks = stats.kstest(np.maximum(rain[:40000, i], 0), stats.gamma(shape[i], scale=scale[i]).cdf)
+        assert ks.pvalue > 1e-3, (i, ks)
+    hv = _env(synthetic.hvac_grid_config(2, 3), prec).native(_dt(prec))
+    assert not ops.env_has_noise_model(hv)                          # HVAC: no noise model in the reference -> deterministic plant
+    xh, uh = _cu(rng.normal(10, 1, size=(64, 6)), prec), _cu(rng.uniform(0, 1, size=(64, 6)), prec)
+    assert torch.equal(ops.env_step_noisy(hv, xh, uh, 1, 2, want_cost=False)[0], ops.env_step(hv, xh, uh, want_cost=False)[0])
+
+
+def test_gymenv_step_is_the_stochastic_plant():
+    """GymEnv.step calls transition(cec=False) like the reference (gymenv.py:18): a Navigation closed loop is noisy by default,
+    reproducible under env.seed(), and noise-free with env.cec_plant = True; the planner's transition() stays deterministic."""
+    from tfmpc_b200 import agents, envs, runners
+    from tfmpc_b200.envs import synthetic
+    from tfmpc_b200.solvers.ilqr import iLQR
+    cfg = synthetic.navigation_config()
+    x0 = np.asarray(cfg["initial_state"], dtype=np.float32)
+    H = 6
+
+    def loop(seed, cec):
+        env = envs.make_env(cfg)
+        env.cec_plant = cec
+        env.seed(seed)
+        with runners.Runner(env, agents.MPC(iLQR(env), H, seed=5))(x0, H) as r:
+            return r.run().states
+    a, b, c, d = loop(11, False), loop(11, False), loop(12, False), loop(11, True)
+    assert np.array_equal(a, b) and not np.array_equal(a, c) and not np.array_equal(a, d)
+    assert np.abs(a - d).max() > 1e-3
+    env = envs.make_env(cfg)
+    s, u = torch.tensor([[0.5], [0.25]]), torch.tensor([[0.1], [-0.2]])
+    assert torch.equal(env.transition(s, u), env.transition(s, u))
+    n1, n2 = env.transition(s, u, cec=False), env.transition(s, u, cec=False)
+    assert n1.shape == (2, 1) and not torch.equal(n1, n2) and (n1 - env.transition(s, u)).abs().max() <= 0.4 + 1e-5
+
+
+def test_start_draws_initial_actions_in_library(prec):
+    """iLQR.start's random initial actions (ilqr.py:59-70) come from the library's device generator: one scalar per step broadcast
+    over the action dimensions (quirk Q4), uniform on [low, high], infinite bounds replaced by -1 / +1, reproducible per seed."""
+    from tfmpc_b200.envs import synthetic
+    from tfmpc_b200.solvers.ilqr import iLQR
+    nav = iLQR(_env(synthetic.navigation_config(), prec), dtype=_dt(prec))
+    u = nav.initial_actions(4096, 50, seed=9)
+    assert u.shape == (4096, 50, 2) and torch.equal(u[..., 0], u[..., 1])
+    assert torch.equal(u, nav.initial_actions(4096, 50, seed=9)) and not torch.equal(u, nav.initial_actions(4096, 50, seed=10))
+    r = _np(u[..., 0]).ravel().astype(np.float64)
+    assert r.min() >= -1 and r.max() <= 1 and abs(r.mean()) < 5e-3 and abs(r.var() - 1 / 3) < 5e-3
+    assert abs(np.corrcoef(r[:-1], r[1:])[0, 1]) < 1e-2
+    free = iLQR(_env(synthetic.navlqr_config([1.0, -2.0, 3.0], 0.5), prec), dtype=_dt(prec))      # unbounded -> [-1, 1]
+    uf = _np(free.initial_actions(512, 7, seed=1))
+    assert uf.shape == (512, 7, 3) and uf.min() >= -1 and uf.max() <= 1 and np.array_equal(uf[..., 0], uf[..., 2])
+    res = iLQR(_env(synthetic.reservoir_config(4), prec), dtype=_dt(prec))                        # [0, 1]
+    ur = _np(res.initial_actions(512, 7, seed=1))
+    assert ur.min() >= 0 and ur.max() <= 1 and abs(ur.mean() - 0.5) < 2e-2
+    xs, us, cs = nav.start(np.zeros((3, 2)), 5, seed=4)
+    assert xs.shape == (3, 6, 2, 1) and torch.equal(us[..., 0], nav.initial_actions(3, 5, seed=4))
 
 
 def test_launchers_and_csv(tmp_path):

@@ -1,7 +1,9 @@
 """Compile the CUDA sources in tfmpc_b200/csrc into the two in-tree shared libraries
 
     tfmpc_b200/lib/libtfmpc_b200.so       tfmpc_real = float   (product build)
-    tfmpc_b200/lib/libtfmpc_b200_f64.so   tfmpc_real = double  (verification build)
+    tfmpc_b200/lib/libtfmpc_b200_f64.so   tfmpc_real = double  (verification build, no FMA contraction)
+    tfmpc_b200/lib_ieee/libtfmpc_b200.so  tfmpc_real = float, IEEE division / sqrt / exp, no flush-to-zero (A/B build: what
+                                          --use_fast_math changes in the product build; loaded only via TFMPC_B200_LIBDIR)
 
 for sm_100a only.  nvcc cross-compiles without a GPU, so this runs in the build container;
 the .so files are git-ignored but travel to the GPU box with the gpurun snapshot.
@@ -15,6 +17,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "lib")
+LIB_IEEE = os.path.join(HERE, "lib_ieee")
 OBJ = os.path.join(HERE, "build")
 SOURCES = ["api.cu", "ilqr_small.cu", "ilqr_queue.cu", "ilqr_warp.cu", "env_ops.cu", "lqr.cu", "peak.cu", "backward_dense.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
@@ -51,21 +54,23 @@ def _compile(args):
     return src, r.returncode, r.stdout + r.stderr
 
 
-def build(force=False, verbose=False, precisions=("f32", "f64")):
+def build(force=False, verbose=False, precisions=("f32", "f64", "f32ieee")):
     os.makedirs(LIB, exist_ok=True)
+    os.makedirs(LIB_IEEE, exist_ok=True)
     os.makedirs(OBJ, exist_ok=True)
     newest = _deps_mtime()
     outputs = {}
     jobs = []
     for prec in precisions:
-        name = "libtfmpc_b200.so" if prec == "f32" else "libtfmpc_b200_f64.so"
-        out = os.path.join(LIB, name)
+        name = "libtfmpc_b200_f64.so" if prec == "f64" else "libtfmpc_b200.so"
+        out = os.path.join(LIB_IEEE if prec == "f32ieee" else LIB, name)
         outputs[prec] = out
         if not force and os.path.exists(out) and os.path.getmtime(out) >= newest:
             continue
         # fp64 verification build: no FMA contraction, so that two code shapes of the same expressions (thread-per-problem,
         # warp-cooperative, tick kernels) and the gcc-built oracle round identically
-        extra = ["-DTFMPC_F64", "-fmad=false"] if prec == "f64" else ([f for f in os.environ.get("TFMPC_F32_FLAGS", F32_FLAGS).split() if f])
+        extra = (["-DTFMPC_F64", "-fmad=false"] if prec == "f64" else [] if prec == "f32ieee" else
+                 [f for f in os.environ.get("TFMPC_F32_FLAGS", F32_FLAGS).split() if f])
         for s in SOURCES:
             jobs.append((os.path.join(CSRC, s), os.path.join(OBJ, f"{os.path.splitext(s)[0]}_{prec}.o"), extra, verbose))
     if jobs:

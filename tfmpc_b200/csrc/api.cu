@@ -187,6 +187,8 @@ int tfmpc_env_create(int kind, int n, int m, int nz, const double *p, int64_t np
       for (int i = 0; i < n; i++) {
         for (int r = 0; r < 6; r++) vec[r * 32 + i] = (real)p[r * n + i];  // cap lb ub lowpen highpen sppen
         vec[6 * 32 + i] = (real)p[6 * n + i] * (real)p[7 * n + i];          // rain = shape * scale (:98-100)
+        vec[7 * 32 + i] = (real)p[6 * n + i];                               // gamma rainfall of the stochastic plant (:102-104)
+        vec[8 * 32 + i] = (real)p[7 * n + i];
         for (int j = 0; j < n; j++) {
           real d_ij = (real)p[8 * n + i * n + j];
           mB[i * 32 + j] = d_ij;  // (D V)_i
@@ -268,6 +270,20 @@ int tfmpc_env_step(const tfmpc_env_t *e, int64_t R, const real *x, const real *u
   REQ(e && x && u && R >= 0, "tfmpc_env_step: bad argument");
   if (R == 0) return TFMPC_OK;
   return env_ops_step(e, R, x, u, xn, cost, (cudaStream_t)stream);
+}
+int tfmpc_env_step_noisy(const tfmpc_env_t *e, int64_t R, const real *x, const real *u, real *xn, real *cost, uint64_t seed, uint64_t offset,
+                         void *stream) {
+  REQ(e && x && u && xn && R >= 0, "tfmpc_env_step_noisy: bad argument");
+  if (R == 0) return TFMPC_OK;
+  int rc = env_ops_step(e, R, x, u, xn, cost, (cudaStream_t)stream);
+  if (rc) return rc;
+  return env_ops_plant_noise(e, R, xn, seed, offset, (cudaStream_t)stream);
+}
+int tfmpc_env_has_noise_model(const tfmpc_env_t *e) { return e && (e->kind == TFMPC_ENV_NAVIGATION || e->kind == TFMPC_ENV_RESERVOIR) ? 1 : 0; }
+int tfmpc_ilqr_initial_actions(const tfmpc_env_t *e, int64_t B, int T, uint64_t seed, real *u_init, void *stream) {
+  REQ(e && u_init && B >= 0 && T >= 1, "tfmpc_ilqr_initial_actions: bad argument");
+  if (B == 0) return TFMPC_OK;
+  return env_ops_initial_actions(e, B, T, seed, u_init, (cudaStream_t)stream);
 }
 int tfmpc_env_final_cost(const tfmpc_env_t *e, int64_t R, const real *x, real *cost, void *stream) {
   REQ(e && x && cost && R >= 0, "tfmpc_env_final_cost: bad argument");

@@ -146,6 +146,8 @@ int warp_ilqr_solve(const tfmpc_env *e, int64_t B, int T, const real *x0, const 
                     real *actions, real *costs, int32_t *stats, void *ws, int64_t ws_bytes, cudaStream_t s);
 
 int env_ops_step(const tfmpc_env *e, int64_t R, const real *x, const real *u, real *xn, real *cost, cudaStream_t s);
+int env_ops_plant_noise(const tfmpc_env *e, int64_t R, real *xn, unsigned long long seed, unsigned long long offset, cudaStream_t s);
+int env_ops_initial_actions(const tfmpc_env *e, int64_t B, int T, unsigned long long seed, real *u_init, cudaStream_t s);
 int env_ops_final_cost(const tfmpc_env *e, int64_t R, const real *x, real *cost, cudaStream_t s);
 int env_ops_linearize(const tfmpc_env *e, int64_t R, const real *x, const real *u, real *f_x, real *f_u, real *l, real *l_x,
                       real *l_u, real *l_xx, real *l_uu, real *l_ux, real *l_xu, cudaStream_t s);

@@ -7,6 +7,7 @@
 // so a warp writes 512 contiguous bytes per matrix.
 // Large environments (Reservoir, HVAC): one warp per row, lane j owns column j, so every
 // [n x n] matrix row is written as one contiguous segment.
+#include "rng.cuh"
 #include "small_core.cuh"
 
 namespace {
@@ -281,6 +282,61 @@ int env_ops_step(const tfmpc_env *e, int64_t R, const real *x, const real *u, re
     if (rc) return rc;
     kl_step<<<grid_warps(R), kThreads, 0, s>>>(e->el, R, x, u, xn, cost, nullptr);
   }
+  LAUNCH_CHECK();
+  return TFMPC_OK;
+}
+
+// ---- stochastic plant (GymEnv.step -> transition(cec=False), reference tfmpc/envs/gymenv.py:18)
+// One thread per state component.  Navigation: x' += truncated normal(0, 0.2) (navigation/__init__.py:45).  Reservoir: the
+// rainfall term of x' (reservoir/__init__.py:57) becomes a Gamma(rain_shape, rain_scale) draw instead of its mean (:98-105),
+// i.e. x' += rain - shape * scale.  The other environments have no noise model in the reference (their transition() takes
+// no `cec` argument).
+__global__ void __launch_bounds__(256) k_plant_noise(int kind, int n, int64_t R, real *xn, const real *vec, unsigned long long seed,
+                                                     unsigned long long offset) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= R * n) return;
+  const int64_t r = idx / n;
+  const int i = (int)(idx - r * n);
+  Philox g(seed ^ (offset * 0x9E3779B97F4A7C15ull), (uint32_t)r, (uint32_t)((uint64_t)r >> 32), (uint32_t)i, 0x504cu);   // tag "PL"ant
+  if (kind == TFMPC_ENV_NAVIGATION) {
+    uint32_t w[4];
+    g.next(w);
+    xn[idx] += (real)(0.2 * trunc_normal2(u01(w[0], w[1])));
+  } else if (kind == TFMPC_ENV_RESERVOIR) {
+    const double shape = (double)vec[7 * 32 + i], scale = (double)vec[8 * 32 + i];
+    xn[idx] += (real)(gamma_draw(g, shape, scale) - shape * scale);
+  }
+}
+
+// ---- iLQR.start's random initial actions (ilqr.py:59-70): ONE uniform scalar per (problem, step), broadcast over the action
+// dimensions, scaled to [low, high] with infinite bounds replaced by -1 / +1
+struct ActionBounds { real lo[MAXD], hi[MAXD]; };
+__global__ void __launch_bounds__(256) k_initial_actions(int m, int64_t BT, ActionBounds b, real *u, unsigned long long seed) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= BT) return;
+  Philox g(seed, (uint32_t)idx, (uint32_t)((uint64_t)idx >> 32), 0u, 0x5354u);   // tag "ST"art
+  uint32_t w[4];
+  g.next(w);
+  const real r = (real)u01(w[0], w[1]);
+  for (int i = 0; i < m; i++) u[idx * m + i] = b.lo[i] + r * (b.hi[i] - b.lo[i]);
+}
+
+int env_ops_plant_noise(const tfmpc_env *e, int64_t R, real *xn, unsigned long long seed, unsigned long long offset, cudaStream_t s) {
+  if (e->kind != TFMPC_ENV_NAVIGATION && e->kind != TFMPC_ENV_RESERVOIR) return TFMPC_OK;   // no noise model in the reference
+  const int64_t items = R * e->n;
+  k_plant_noise<<<(unsigned)((items + 255) / 256), 256, 0, s>>>(e->kind, e->n, R, xn, e->el.vec, seed, offset);
+  LAUNCH_CHECK();
+  return TFMPC_OK;
+}
+
+int env_ops_initial_actions(const tfmpc_env *e, int64_t B, int T, unsigned long long seed, real *u_init, cudaStream_t s) {
+  ActionBounds b;
+  for (int i = 0; i < e->m; i++) {
+    b.lo[i] = (real)(std::isinf(e->low[i]) ? -1.0 : e->low[i]);
+    b.hi[i] = (real)(std::isinf(e->high[i]) ? 1.0 : e->high[i]);
+  }
+  const int64_t items = B * T;
+  k_initial_actions<<<(unsigned)((items + 255) / 256), 256, 0, s>>>(e->m, items, b, u_init, seed);
   LAUNCH_CHECK();
   return TFMPC_OK;
 }

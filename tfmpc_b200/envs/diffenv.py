@@ -1,6 +1,7 @@
 """DiffEnv: the differentiable-environment interface of the reference
 (tfmpc/envs/diffenv.py:6-101) backed by analytic CUDA linearisation kernels instead of
 GradientTape autodiff."""
+import os
 from collections import namedtuple
 
 import numpy as np
@@ -66,11 +67,18 @@ class DiffEnv:
 
     # -- reference API -------------------------------------------------------------------
     def transition(self, state, action, batch=False, cec=True):
-        if not cec:
-            raise NotImplementedError("stochastic (cec=False) plant dynamics are provided by tfmpc_b200.envs.gymenv.GymEnv")
+        """cec=True: the deterministic dynamics the planner uses.  cec=False: the plant -- the environment's noise model on
+        (navigation/__init__.py:45, reservoir/__init__.py:98-105), drawn on the device; every call advances the draw counter,
+        `seed()` (GymEnv) restarts it.  Environments without a noise model ignore the flag."""
         x, single, col = self._rows(state, self.state_size)
         u, _, _ = self._rows(action, self.action_size)
-        xn, _ = ops.env_step(self.native(), x, u, want_cost=False)
+        if cec:
+            xn, _ = ops.env_step(self.native(), x, u, want_cost=False)
+        else:
+            if getattr(self, "_noise_seed", None) is None:
+                self._noise_seed, self._noise_calls = int.from_bytes(os.urandom(8), "little"), 0
+            xn, _ = ops.env_step_noisy(self.native(), x, u, self._noise_seed, self._noise_calls, want_cost=False)
+            self._noise_calls += 1
         xn = xn[0] if single else xn
         return xn.unsqueeze(-1) if col else xn
 

@@ -32,17 +32,6 @@ class Navigation(DiffEnv, GymEnv):
              + list(self.deceleration["center"].reshape(-1)) + list(self.deceleration["decay"]))
         return nz, p
 
-    stochastic = False  # set True for the reference's cec=False plant (gymenv.py:18)
-
-    def _plant_noise(self, state, action, next_state):
-        """truncated-normal position noise, sigma = 0.2 (navigation/__init__.py:44-46)"""
-        if not self.stochastic:
-            return next_state
-        import torch
-        noise = torch.empty_like(next_state)
-        torch.nn.init.trunc_normal_(noise, mean=0.0, std=0.2, a=-0.4, b=0.4)
-        return next_state + noise
-
     def __repr__(self):
         goal = self.goal.squeeze().tolist()
         bounds = f"[{self.action_space.low.squeeze().tolist()}, {self.action_space.high.squeeze().tolist()}]"

@@ -37,21 +37,6 @@ class Reservoir(DiffEnv, GymEnv):
             p += list(getattr(self, k).reshape(-1))
         return 0, p + list(self.downstream.reshape(-1))
 
-    stochastic = False  # set True for the reference's cec=False plant (gymenv.py:18)
-
-    def _plant_noise(self, state, action, next_state):
-        """gamma rainfall instead of its mean (reservoir/__init__.py:98-105)"""
-        if not self.stochastic:
-            return next_state
-        import torch
-        shape = torch.as_tensor(self.rain_shape.reshape(-1), dtype=next_state.dtype, device=next_state.device)
-        scale = torch.as_tensor(self.rain_scale.reshape(-1), dtype=next_state.dtype, device=next_state.device)
-        col = next_state.dim() >= 2 and next_state.shape[-1] == 1
-        base = next_state.squeeze(-1) if col else next_state
-        rain = torch.distributions.Gamma(shape, 1.0 / scale).sample(base.shape[:-1])
-        out = base + (rain - shape * scale)
-        return out.unsqueeze(-1) if col else out
-
     def __repr__(self):
         return f"Reservoir({self.state_size})"
 

@@ -33,6 +33,7 @@ def online_ilqr_run(config):
     config = dict(config)
     env, x0, T = _load(config)
     solver = ilqr.iLQR(env, **config)
+    env.seed(config.get("seed"))       # the plant is the stochastic one (GymEnv.step -> transition(cec=False), gymenv.py:18)
     controller = agents.MPC(solver, T, seed=config.get("seed"))
     runner = runners.Runner(env, controller)
     with runner(x0, T) as r:

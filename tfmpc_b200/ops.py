@@ -109,6 +109,33 @@ def env_step(env, x, u, want_next=True, want_cost=True):
     return xn, cost
 
 
+def env_step_noisy(env, x, u, seed, offset, want_cost=True):
+    """tfmpc_env_step_noisy: the plant of GymEnv.step (transition(cec=False)): x [R,n], u [R,m] -> (x_next, cost | None) with the
+    environment's noise model drawn on the device (Philox keyed by `seed`, call number `offset`)."""
+    x, u = _c(x), _c(u)
+    R = x.shape[0]
+    lib = env.lib
+    xn = _empty(x, R, env.n)
+    cost = _empty(x, R) if want_cost else None
+    px, pu, pn, pc = (N.dev_ptr(lib, t) for t in (x, u, xn, cost))
+    N.check(lib, lib.tfmpc_env_step_noisy(env.handle, C.c_int64(R), px.p, pu.p, pn.p, pc.p, C.c_uint64(int(seed) & (2 ** 64 - 1)),
+                                          C.c_uint64(int(offset)), N.stream_ptr()))
+    return xn, cost
+
+
+def env_has_noise_model(env):
+    return bool(env.lib.tfmpc_env_has_noise_model(env.handle))
+
+
+def ilqr_initial_actions(env, B, T, seed, dtype, device):
+    """tfmpc_ilqr_initial_actions: iLQR.start's random initial actions [B,T,m], drawn on the device."""
+    u = torch.empty(int(B), int(T), env.m, dtype=dtype, device=device)
+    lib = env.lib
+    pu = N.dev_ptr(lib, u)
+    N.check(lib, lib.tfmpc_ilqr_initial_actions(env.handle, C.c_int64(int(B)), int(T), C.c_uint64(int(seed) & (2 ** 64 - 1)), pu.p, N.stream_ptr()))
+    return u
+
+
 def env_final_cost(env, x):
     x = _c(x)
     R = x.shape[0]

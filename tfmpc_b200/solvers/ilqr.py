@@ -81,18 +81,11 @@ class iLQR:
 
     def initial_actions(self, batch, T, seed=None):
         """The reference's random start: ONE U(0,1) scalar per step, scaled to [low, high] in every
-        action dimension, +-inf bounds replaced by +-1 (ilqr.py:59-70)."""
-        low = np.asarray(self.env.action_space.low, dtype=np.float64).reshape(-1)
-        high = np.asarray(self.env.action_space.high, dtype=np.float64).reshape(-1)
-        lo = torch.as_tensor(np.where(np.isinf(low), -1.0, low), dtype=self.dtype, device=self._dev())
-        hi = torch.as_tensor(np.where(np.isinf(high), 1.0, high), dtype=self.dtype, device=self._dev())
-        gen = torch.Generator(device=self._dev())
+        action dimension, +-inf bounds replaced by +-1 (ilqr.py:59-70), drawn by the library
+        on the device (tfmpc_ilqr_initial_actions: Philox keyed by `seed`; unseeded = a fresh seed from the OS)."""
         if seed is None:
-            gen.seed()
-        else:
-            gen.manual_seed(int(seed))
-        r = torch.rand(batch, int(T), 1, generator=gen, device=self._dev(), dtype=self.dtype)
-        return (lo + r * (hi - lo)).contiguous()
+            seed = int.from_bytes(os.urandom(8), "little")
+        return ops.ilqr_initial_actions(self._native(), batch, T, seed, self.dtype, self._dev())
 
     # -- stages --------------------------------------------------------------------------
     def start(self, x0, T, u_init=None, seed=None):

@@ -132,14 +132,15 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
 
 
-def cpu_baseline(name, T, sample, threads=0, repeats=1, want_result=False):
+def cpu_baseline(name, T, sample, threads=0, repeats=1, want_result=False, batch=0):
     """The CPU arm: the oracle port (C, OpenMP over problems) on the host cores, on a bounded sample of the
     same workload -- the first `sample` problems of the GPU arm's rank-0 batch.  Returns (problem-iterations/s, cores,
     problem-iterations, seconds[, oracle result])."""
     from oracle import oracle
     o = oracle.Oracle("f32")
     cfg = workload_cfg(name)
-    x0, u0 = make_inputs(cfg, sample, T, seed=1000)
+    x0, u0 = make_inputs(cfg, max(batch, sample), T, seed=1000)      # the generator draws the whole batch: slice, do not re-draw
+    x0, u0 = np.ascontiguousarray(x0[:sample]), np.ascontiguousarray(u0[:sample])
     env = o.make_env(cfg)
     cores = max(o.max_threads(), len(os.sched_getaffinity(0))) if threads <= 0 else threads   # every host core the process may use
     best, res = None, None
@@ -372,7 +373,7 @@ def run_reference(args):
         sample = f"{B} problems per step, {args.steps} steps"
     else:
         sample_n = args.cpu_sample or {"c3": B_full, "c4": 512, "c5s": 128, "c5": 16}[name]
-        run = (lambda n: cpu_mpc_loop(T, n)) if name == "c5" else (lambda n: cpu_baseline(name, T, n))
+        run = (lambda n: cpu_mpc_loop(T, n)) if name == "c5" else (lambda n: cpu_baseline(name, T, n, batch=B_full))
         for _ in range(args.warmup):
             run(max(8 if name == "c5" else 64, sample_n // 8))
         secs, pis = 0.0, 0.0
@@ -700,7 +701,7 @@ def run_ours(args):
             if name == "c5":
                 v, cores, pi, dt = cpu_mpc_loop(T, sample)
             else:
-                v, cores, pi, dt, res = cpu_baseline(name, T, sample, want_result=True)
+                v, cores, pi, dt, res = cpu_baseline(name, T, sample, want_result=True, batch=B)
                 line["parity"] = parity_block(stats, totals, res)
             line["cpu_baseline"] = {"value": v, "unit": "problem-iterations/s", "cores": cores, "kind": "port",
                                     "sample": f"the first {sample} problems of the timed batch ({pi:.0f} problem-iterations in {dt:.1f} s), "

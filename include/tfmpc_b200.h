@@ -72,7 +72,11 @@ enum {
   TFMPC_ST_NONPD = 2,       /* a box-QP / inverse factorisation failed (optimization.py:47-51; the reference aborts) */
   TFMPC_ST_REGLOOP = 3,     /* regularisation loop guard tripped (the reference would spin, ilqr.py:238) */
   TFMPC_ST_NAN = 4,         /* NaN in the gradient norm */
-  TFMPC_ST_ABORTED = 5      /* the solve kernel gave up before this problem finished (device watchdog); results undefined */
+  TFMPC_ST_ABORTED = 5,     /* the solve kernel gave up before this problem finished (device watchdog); results undefined */
+  TFMPC_ST_TICKS = 6        /* per-tick launch sequence only (option "solver" = 0): the fixed budget of max_iterations + 24 ticks ran
+                             * out before the problem finished (more than 24 rejected line searches in total); the trajectory is the
+                             * last nominal.  The work-queue, lane-per-state and dense solvers have no such budget: they allow the
+                             * reference's unbounded retries up to the 200-per-iteration guard of TFMPC_ST_REGLOOP. */
 };
 
 typedef struct tfmpc_env tfmpc_env_t; /* opaque */

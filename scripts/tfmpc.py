@@ -101,11 +101,13 @@ def ilqr(**kwargs):
     kwargs.pop("num_workers")
     seed = kwargs.pop("seed")
     exec_func = online_ilqr_run if online else ilqr_run
+    config = dict(kwargs)
+    if seed is not None:
+        config["seed"] = seed
+    # the reference fans the samples out over worker processes (tuneconfig); here they are ONE batch on the GPU
+    _, batch = exec_func(config, num_samples=num_samples)
     for run_id in range(num_samples):
-        config = dict(kwargs, run_id=run_id, logdir=os.path.join(kwargs["logdir"], f"run{run_id}"))
-        if seed is not None:
-            config["seed"] = seed + run_id
-        _, trajectory = exec_func(config)
+        trajectory = batch[run_id]
         print(repr(trajectory))
         print(str(trajectory))
 

@@ -825,6 +825,31 @@ def test_cli_commands(tmp_path):
                          capture_output=True, text=True)
     assert out.returncode == 0, out.stderr
     assert out.stdout.count("Trajectory(init=") == 2 and os.path.exists(tmp_path / "log" / "run1" / "data.csv")
+    # the samples are ONE batch on the GPU (two launches: queue init + solve), not one solve per sample; they differ (independent initial actions)
+    import pandas as pd
+    r0, r1 = (pd.read_csv(tmp_path / "log" / f"run{i}" / "data.csv") for i in (0, 1))
+    assert len(r0) == len(r1) == 10 and not np.allclose(r0["u[1]"].values, r1["u[1]"].values)
+    out = subprocess.run([sys.executable, cli, "ilqr", str(path), "--online", "-hr", "4", "--logdir", str(tmp_path / "on"), "--seed", "1", "-ns", "3"],
+                         capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    assert out.stdout.count("Trajectory(init=") == 3 and os.path.exists(tmp_path / "on" / "run2" / "data.csv")
+
+
+def test_launchers_batch_samples_are_one_solve(tmp_path):
+    """`--num-samples N` (scripts/tfmpc.py:203-210 in the reference: N runs fanned out over worker processes) is a batch axis here:
+    ilqr_run(config, num_samples=N) issues ONE solve for the N samples."""
+    from tfmpc_b200 import _native
+    from tfmpc_b200.envs import synthetic
+    from tfmpc_b200.launchers import ilqr_run
+    path = tmp_path / "nav.json"
+    path.write_text(json.dumps(synthetic.navigation_config()))
+    ilqr_run({"env": str(path), "horizon": 8, "seed": 3}, num_samples=2)          # warm (allocations)
+    before = _native.kernel_launch_count("f32")
+    env, batch = ilqr_run({"env": str(path), "horizon": 8, "seed": 3, "logdir": str(tmp_path / "s")}, num_samples=64)
+    launches = _native.kernel_launch_count("f32") - before
+    assert len(batch) == 64 and batch.states.shape == (64, 9, 2) and launches <= 4, launches     # initial actions + queue init + solve
+    assert os.path.exists(tmp_path / "s" / "run63" / "data.csv")
+    assert len(np.unique(np.round(batch.total_cost, 4))) > 32                     # independent samples
 
 
 def test_lqr_dump_load_roundtrip(tmp_path):

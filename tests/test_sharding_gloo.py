@@ -65,3 +65,31 @@ def test_sharded_solve_and_gather_world2(B):
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, port, B, ret), nprocs=world, join=True)
     assert dict(ret) == {0: True, 1: True}
+
+
+def _worker_full(rank, world, port, B, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from tfmpc_b200.sharding import gather_results, shard_range
+        T, n, m = 5, 2, 2
+        g = torch.Generator().manual_seed(0)        # the same global results on every rank; each rank contributes its block
+        glob = {"states": torch.rand(B, T + 1, n, generator=g), "actions": torch.rand(B, T, m, generator=g),
+                "costs": torch.rand(B, T + 1, generator=g), "stats": torch.randint(0, 100, (B, 4), generator=g, dtype=torch.int32)}
+        lo, hi = shard_range(B, rank, world)
+        full = gather_results({k: v[lo:hi].clone() for k, v in glob.items()}, B)
+        ret[rank] = all(full[k].shape == glob[k].shape and torch.equal(full[k], glob[k]) for k in glob)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("B", [8, 11, 2])
+def test_full_result_gather_world2(B):
+    """sharding.gather_results: one all_gather_into_tensor per buffer (states, actions, costs, stats) of RAGGED shards (padded to
+    the largest block) reassembles the full batch on every rank -- the gather SURVEY section 8(e) describes."""
+    world, port = 2, _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker_full, args=(world, port, B, ret), nprocs=world, join=True)
+    assert dict(ret) == {0: True, 1: True}

@@ -22,7 +22,7 @@ _LIBS = {}
 _LOCK = threading.Lock()
 
 ENV_KIND = {"NavigationLQR": 0, "Navigation": 1, "Reservoir": 2, "HVAC": 3}
-STATUS = {0: "converged", 1: "max_iterations", 2: "non_pd", 3: "regularisation_loop", 4: "nan", 5: "aborted"}
+STATUS = {0: "converged", 1: "max_iterations", 2: "non_pd", 3: "regularisation_loop", 4: "nan", 5: "aborted", 6: "tick_budget"}
 
 
 class TfmpcError(RuntimeError):

@@ -19,7 +19,9 @@ typedef tfmpc_real real;
 #endif
 
 // ---- scalar math in the build's precision.  The fp32 product library is compiled with --use_fast_math (build.py:
-// MUFU-based division / exp / sqrt, FTZ), the fp64 verification build is IEEE; DESIGN.md "numerics" has the parity data.
+// MUFU-based division / exp / sqrt, FTZ), the fp64 verification build is IEEE without FMA contraction, and lib_ieee/ holds an IEEE
+// fp32 build of the same sources for the A/B of tests/test_gpu_fullsize.py::test_c3_fast_math_does_not_create_failures
+// (status codes and iteration counts of the whole C3 batch, both builds against the oracle); DESIGN.md "numerics" has the data.
 HD real r_abs(real v) { return v < 0 ? -v : v; }
 HD real r_max(real a, real b) { return a > b ? a : b; }
 HD real r_min(real a, real b) { return a < b ? a : b; }

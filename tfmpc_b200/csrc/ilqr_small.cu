@@ -345,7 +345,7 @@ __global__ void __launch_bounds__(kThreads) k_costs(EnvSmall e, int64_t B, int T
   nom.load_x(T, x);
   w.cost[(int64_t)T * w.S + b] = env_final_cost<KIND, N, M>(e, x);
   int st = w.status[b];
-  if (w.phase[b] != PH_DONE) st = TFMPC_ST_REGLOOP;  // ran out of ticks (more than kExtraTicks rejected line searches)
+  if (w.phase[b] != PH_DONE) st = TFMPC_ST_TICKS;  // ran out of ticks (more than kExtraTicks rejected line searches in total)
   reinterpret_cast<int4 *>(stats)[b] = make_int4(w.iteration[b], w.n_bwd[b], w.n_fwd[b], st);
 }
 
@@ -659,7 +659,9 @@ static int solve_launch(const tfmpc_env *e, int64_t B, int T, const real *x0, co
     cudaEventDestroy(fork);   // released by the runtime once the recorded work has completed
     cudaEventDestroy(join);
   } else if (done) cudaEventRecord(done, s);
-  tfmpc_count_launch(2 * ticks + 4);
+  // kernels executed by this solve, launched directly or replayed from the two captured graphs: k_init, two per tick, k_costs
+  // and three k_transpose_out (the same sequence in both cases; a graph replay runs its kernel nodes, it does not skip any)
+  tfmpc_count_launch(1 + 2 * ticks + 1 + 3);
   return TFMPC_OK;
 }
 
@@ -680,7 +682,10 @@ int small_ilqr_solve(const tfmpc_env *e, int64_t B, int T, const real *x0, const
 #define CALL(KD, N, M) { int rc_ = solve_launch<KD, N, M>(e, B, T, x0, u_init, o, states, actions, costs, stats, ws, s, done); if (rc_) return rc_; }
   SMALL_DISPATCH(e, CALL);
 #undef CALL
-  LAUNCH_CHECK();
+  {   // (the launches were counted by solve_launch)
+    cudaError_t err_ = cudaGetLastError();
+    if (err_ != cudaSuccess) return tfmpc_set_error(TFMPC_E_CUDA, "CUDA launch failed: %s", cudaGetErrorString(err_));
+  }
   return TFMPC_OK;
 }
 

@@ -11,6 +11,7 @@ Differences, all additive:
 """
 import logging
 import os
+import warnings
 from collections import namedtuple
 
 import numpy as np
@@ -174,6 +175,9 @@ class iLQR:
         stats = out["stats"].cpu().numpy()
         logging.info(f"[SOLVE] mean iterations={stats[:, 0].mean():.2f} status={np.bincount(stats[:, 3], minlength=5).tolist()}")
         if single:
+            if int(stats[0, 3]) not in (0, 1):      # not converged / max_iterations: the reference would have raised or exited (ilqr.py:305-313)
+                warnings.warn(f"iLQR.solve stopped with status '{N.STATUS.get(int(stats[0, 3]), stats[0, 3])}' at iteration {int(stats[0, 0])}; "
+                              "the trajectory returned is the last nominal", RuntimeWarning, stacklevel=2)
             return trajectory.Trajectory(out["states"][0], out["actions"][0], out["costs"][0]), int(stats[0, 0])
         return (trajectory.BatchTrajectory(out["states"], out["actions"], out["costs"], iterations=stats[:, 0], status=stats[:, 3]),
                 stats[:, 0].copy())

@@ -76,12 +76,26 @@ class LQR:
     def _lib(self):
         return N.load("f32" if self.dtype == torch.float32 else "f64")
 
+    def _match_batch(self, t, what):
+        """A batched solver (per-problem F / f / C / c) takes one row per problem, or a single row that is shared by all of them;
+        anything else would index the parameters out of bounds on the device."""
+        B = self.batch_size
+        if B is None or t is None or t.shape[0] == B:
+            return t
+        if t.shape[0] == 1:
+            return t.expand(B, *t.shape[1:]).contiguous()
+        raise N.TfmpcError(f"{what}: {t.shape[0]} rows for a solver of {B} problems (expected {B}, or 1 to share)")
+
     def _step(self, x, u, want):
         n, m = self.state_size, self.action_size
         F, f, Cm, c = self._device_params()
         sF, sf, sC, sc = self._strides()
         xr, single = self._x(x, n)
         ur = self._x(u, m)[0] if u is not None else None
+        xr, ur = self._match_batch(xr, "state"), self._match_batch(ur, "action")
+        if ur is not None and ur.shape[0] != xr.shape[0]:
+            raise N.TfmpcError(f"{ur.shape[0]} actions for {xr.shape[0]} states")
+        single = single and xr.shape[0] == 1
         R = xr.shape[0]
         lib = self._lib()
         outs = {k: (torch.empty((R, n) if k == "next" else (R,), dtype=self.dtype, device=xr.device) if k == want else None)
@@ -134,6 +148,8 @@ class LQR:
         F, f, Cm, c = self._device_params()
         sF, sf, sC, sc = self._strides()
         x0r, single = self._x(x0, n)
+        x0r = self._match_batch(x0r, "x0")
+        single = single and x0r.shape[0] == 1
         B = x0r.shape[0]
         T = int(T)
         K = torch.stack([torch.as_tensor(p[0]) for p in policy], dim=-3).to(device=x0r.device, dtype=self.dtype).reshape(-1, T, m, n)
@@ -141,6 +157,8 @@ class LQR:
         k = k.to(device=x0r.device, dtype=self.dtype).reshape(-1, T, m)
         if K.shape[0] == 1 and B > 1:
             K, k = K.expand(B, -1, -1, -1), k.expand(B, -1, -1)
+        if K.shape[0] != B or k.shape[0] != B:
+            raise N.TfmpcError(f"policy of {K.shape[0]} problems for {B} initial states")
         K, k = K.contiguous(), k.contiguous()
         lib = self._lib()
         states = torch.empty(B, T + 1, n, dtype=self.dtype, device=x0r.device)
@@ -160,6 +178,8 @@ class LQR:
         """lqr.py:163-166 -> Trajectory (single problem) or BatchTrajectory"""
         out, single = self._solve(x0, T, terminal_zero, want_policy=False, want_value=False)
         if single:
+            if int(out["status"][0]) != 0:     # the reference raises here too (tf.linalg.inv of a singular Q_uu, lqr.py:84)
+                raise N.TfmpcError("LQR.solve: Q_uu is singular at some timestep (status %d)" % int(out["status"][0]))
             return trajectory.Trajectory(out["states"][0], out["actions"][0], out["costs"][0])
         return trajectory.BatchTrajectory(out["states"], out["actions"], out["costs"], status=out["status"])
 

@@ -232,7 +232,7 @@ int tfmpc_ilqr_solve(const tfmpc_env_t *env, int64_t B, int T, const tfmpc_real 
  *   "qp"                 box-QP of the constrained controller (ilqr.py:364-387) for m <= 2:
  *                        2 = closed form (default of the fp32 build), 0 = the reference's projected-Newton iteration
  *                        (optimization.py:6-101; default of the fp64 verification build)                        TFMPC_QP=closed|newton
- *   "queue_warps_per_sm" resident warps per SM of the queue kernel (default 18)                                  TFMPC_QUEUE_WPS
+ *   "queue_warps_per_sm" resident warps per SM of the queue kernel (<= 18; 0 = the mode decides: 18 / 14)           TFMPC_QUEUE_WPS
  *   "queue_mode"         scheduling policy of the queue kernel: 1 = throughput (several batches in flight: the last
  *                        problems of a batch stay in full warps, one per SM), 2 = latency (a batch that has the GPU to
  *                        itself: the last problems spread over every warp slot and, once there are fewer problems than

@@ -18,6 +18,7 @@ constexpr int kMaxWarpsPerSM = 8;    // WarpSmem is 23 KB in the fp64 build (n =
 constexpr int kMaxWarpsPerSM = 18;   // 11.8 KB of shared memory per warp (n = m = 2) and 96 registers per thread (no spills): measured
                                      // 337 M problem-iterations/s against 306 at 16 warps / 106 registers (profiles/r02_ab_queue.txt)
 #endif
+constexpr int kLatencyWarpsPerSM = kMaxWarpsPerSM < 14 ? kMaxWarpsPerSM : 14;
 
 template <int KIND, int N, int M, int QP>
 __global__ void __launch_bounds__(32, kMaxWarpsPerSM) k_queue_solve(EnvSmall e, IlqrOpts o, tq::QParams q) {
@@ -38,14 +39,16 @@ int env_int(const char *name, int dflt) {
   return v && *v ? atoi(v) : dflt;
 }
 
-std::atomic<int> g_wps{env_int("TFMPC_QUEUE_WPS", kMaxWarpsPerSM)};
+std::atomic<int> g_wps{env_int("TFMPC_QUEUE_WPS", 0)};   // 0 = the mode decides
 // Scheduling policy.  The same kernel serves two regimes that want opposite things from the last few thousand problems of a
 // batch: with several batches in flight (pipelined throughput) the stragglers should occupy as few warps as possible --
 // full warps, one per SM, lane-per-problem -- because every other warp slot is doing another batch's bulk work; a batch
 // that has the GPU to itself (latency) should spread them over all warp slots and, once there are fewer problems than
 // slots, give each problem a whole warp (the solo engine: ~34 us per iteration against ~75 us on one lane).
-//   mode 1 = throughput: pop-size target = one warp per SM, solo engine off
-//   mode 2 = latency:    pop-size target = 12 warps per SM, solo once unfinished <= warp slots
+//   mode 1 = throughput: 18 resident warps per SM, pop-size target = one warp per SM, solo engine off
+//   mode 2 = latency:    14 resident warps per SM (the lone batch is bound by the latency of a warp iteration, which contention
+//                        for the issue slots stretches: 8.14 ms at 18 warps, 7.98 at 16, 7.83 at 14, 7.89 at 12), pop-size target =
+//                        12 warps per SM, solo once unfinished <= launched warps
 //   mode 0 = auto:       latency when no other stream of this device has a queue solve in flight at launch time
 // Each of the knobs below overrides the mode's choice when set (> 0; solo_max: anything but 255).
 std::atomic<int> g_mode{env_int("TFMPC_QUEUE_MODE", 0)};
@@ -112,8 +115,7 @@ Plan make_plan(const tfmpc_env *e, int64_t B, int T) {
   p.NL = ((T + 1) * chn + tq::CPH - 1) / tq::CPH;   // half-lines per trajectory row
   p.row_r4 = p.NL * tq::CPH;
   p.ch2 = (m * n + m + 1) / 2;
-  const int wps = std::max(1, std::min(g_wps.load(), kMaxWarpsPerSM));
-  p.nwarps = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)device_sms(e->device) * wps, B));
+  p.nwarps = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)device_sms(e->device) * kMaxWarpsPerSM, B));   // the layout is sized for the most warps a launch may use
   p.cap = 1024;
   while (p.cap < 2u * (unsigned)B) p.cap <<= 1;
   auto al = [](int64_t v) { return (v + 255) / 256 * 256; };
@@ -150,21 +152,23 @@ int launch(const tfmpc_env *e, int64_t B, int T, const real *x0, const real *u_i
   if (!capturing) lock.lock();
   if (mode != 1 && mode != 2) mode = (capturing || others_in_flight(e->device, s)) ? 1 : 2;
   g_last_mode.store(mode);
-  const int sms = device_sms(e->device), wt = g_w_target.load(), ws_ = g_w_solo.load(), sm_ = g_solo_max.load();
+  const int sms = device_sms(e->device), wt = g_w_target.load(), ws_ = g_w_solo.load(), sm_ = g_solo_max.load(), wp_ = g_wps.load();
+  const int wps = std::max(1, std::min(wp_ > 0 ? wp_ : (mode == 2 ? kLatencyWarpsPerSM : kMaxWarpsPerSM), kMaxWarpsPerSM));
+  const int nwarps = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)sms * wps, B));   // warps (= CTAs) of this launch
   q.w_target = wt > 0 ? wt : (mode == 2 ? 12 * sms : sms);
   q.patience = std::max(0, g_patience.load());
   q.solo_max = std::max(0, std::min(32, sm_ != 255 ? sm_ : (mode == 2 ? 1 : 0)));
-  q.w_solo = q.solo_max > 0 ? (ws_ > 0 ? ws_ : (mode == 2 ? pl.nwarps : q.w_target)) : 0;
+  q.w_solo = q.solo_max > 0 ? (ws_ > 0 ? ws_ : (mode == 2 ? nwarps : q.w_target)) : 0;
   q.watchdog_ns = 4000000000ull;   // 4 s without progress for one warp: give up (status TFMPC_ST_ABORTED) instead of hanging the device
   q.x0 = x0; q.u_init = u_init; q.states = states; q.actions = actions; q.costs = costs; q.stats = stats;
   q.trace = g_trace.load() ? (unsigned *)(base + pl.o_trace) : nullptr;
   q.trace_cap = kTraceCap;
   const int64_t init_items = std::max<int64_t>(std::max<int64_t>(B, (int64_t)pl.cap), tq::C_INTS);
-  k_queue_init<<<(unsigned)((init_items + 255) / 256), 256, 0, s>>>(q, pl.nwarps);
+  k_queue_init<<<(unsigned)((init_items + 255) / 256), 256, 0, s>>>(q, nwarps);
   LAUNCH_CHECK();
   constexpr bool can_close = M <= 2;
-  if (can_close && qp == QP_CLOSED) k_queue_solve<KIND, N, M, (M <= 2 ? QP_CLOSED : QP_NEWTON)><<<pl.nwarps, 32, 0, s>>>(e->es, o, q);
-  else k_queue_solve<KIND, N, M, QP_NEWTON><<<pl.nwarps, 32, 0, s>>>(e->es, o, q);
+  if (can_close && qp == QP_CLOSED) k_queue_solve<KIND, N, M, (M <= 2 ? QP_CLOSED : QP_NEWTON)><<<nwarps, 32, 0, s>>>(e->es, o, q);
+  else k_queue_solve<KIND, N, M, QP_NEWTON><<<nwarps, 32, 0, s>>>(e->es, o, q);
   LAUNCH_CHECK();
   if (!capturing) note_in_flight(e->device, s);
   return TFMPC_OK;

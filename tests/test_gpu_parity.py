@@ -849,8 +849,8 @@ def test_launchers_batch_samples_are_one_solve(tmp_path):
     launches = _native.kernel_launch_count("f32") - before
     assert len(batch) == 64 and batch.states.shape == (64, 9, 2) and launches <= 4, launches     # initial actions + queue init + solve
     assert os.path.exists(tmp_path / "s" / "run63" / "data.csv")
-    # independent initial action sequences, one optimum: the samples take different numbers of iterations to the same cost
-    assert np.allclose(batch.total_cost, batch.total_cost[0], rtol=1e-3) and len(np.unique(batch.iterations)) > 1
+    # independent initial action sequences, one optimum (the actions saturate on the way to the far goal): same converged cost
+    assert np.allclose(batch.total_cost, batch.total_cost[0], rtol=1e-3) and (batch.status == 0).all()
 
 
 def test_lqr_dump_load_roundtrip(tmp_path):

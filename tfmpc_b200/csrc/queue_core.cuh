@@ -340,6 +340,27 @@ WD void rollout_round(WarpRT &rt, WarpSmem &sm, const EnvSmall &e, int T, int NH
   rt.template cp_wait<0>();
 }
 
+// Results of one finished problem in the reference layouts (states [B,T+1,n], actions [B,T,m], costs [B,T+1]), written by
+// the whole warp: lane t handles timesteps t, t + 32, ... of the nominal `nom` (shared or global memory).
+template <int KIND, int N, int M>
+WD void write_results(WarpRT &rt, const EnvSmall &e, const QParams &q, int b, const VecTraj<N, M> &nom) {
+  const int T = q.T;
+  real *Sx = q.states + (int64_t)b * (T + 1) * N, *A = q.actions + (int64_t)b * T * M, *Cc = q.costs + (int64_t)b * (T + 1);
+  for (int t = rt.lane; t <= T; t += 32) {
+    real x[N], u[M];
+    nom.load_xu(t, x, u);
+#pragma unroll
+    for (int i = 0; i < N; i++) Sx[t * N + i] = x[i];
+    if (t < T) {
+#pragma unroll
+      for (int i = 0; i < M; i++) A[t * M + i] = u[i];
+      Cc[t] = env_cost<KIND, N, M>(e, x, u);
+    } else {
+      Cc[T] = env_final_cost<KIND, N, M>(e, x);
+    }
+  }
+}
+
 // ================================================================== the solo engine (see the header comment)
 template <int N, int M>
 struct Solo {
@@ -633,21 +654,8 @@ WD bool solo_run(WarpRT &rt, WarpSmem &sm, const EnvSmall &e, const IlqrOpts &o,
       return false;
     }
   }
-  // ---- finished: results in the reference layouts (states [B,T+1,n], actions [B,T,m], costs [B,T+1])
-  real *Sx = q.states + (int64_t)b * (T + 1) * N, *A = q.actions + (int64_t)b * T * M, *Cc = q.costs + (int64_t)b * (T + 1);
-  for (int t = lane; t <= T; t += 32) {
-    real x[N], u[M];
-    nom.load_xu(t, x, u);
-#pragma unroll
-    for (int i = 0; i < N; i++) Sx[t * N + i] = x[i];
-    if (t < T) {
-#pragma unroll
-      for (int i = 0; i < M; i++) A[t * M + i] = u[i];
-      Cc[t] = env_cost<KIND, N, M>(e, x, u);
-    } else {
-      Cc[T] = env_final_cost<KIND, N, M>(e, x);
-    }
-  }
+  // ---- finished
+  write_results<KIND, N, M>(rt, e, q, b, nom);
   if (lane == 0) {
     int32_t *st = q.stats + (int64_t)b * 4;
     st[0] = p.iteration; st[1] = p.n_bwd; st[2] = p.n_fwd; st[3] = p.status;
@@ -868,22 +876,14 @@ WD void queue_warp_main(WarpRT &rt, const EnvSmall &e, const IlqrOpts &o, const 
     rt.fence();      // trajectory lines were written by other lanes of the warp (and must be visible grid-wide before the ticket is)
     rt.syncwarp();
     keep = valid && p.phase != PH_DONE;
-    if (valid && !keep) {   // finished: results in the reference layouts (states [B,T+1,n], actions [B,T,m], costs [B,T+1])
-      const VecTraj<N, M> nom = {traj_row(q, p.cur, b), CHn, 1};
-      real *S = q.states + (int64_t)b * (T + 1) * N, *A = q.actions + (int64_t)b * T * M, *Cc = q.costs + (int64_t)b * (T + 1);
-      real x[N], u[M];
-      for (int t = 0; t < T; t++) {
-        nom.load_xu(t, x, u);
-#pragma unroll
-        for (int i = 0; i < N; i++) S[t * N + i] = x[i];
-#pragma unroll
-        for (int i = 0; i < M; i++) A[t * M + i] = u[i];
-        Cc[t] = env_cost<KIND, N, M>(e, x, u);
-      }
-      nom.load_x(T, x);
-#pragma unroll
-      for (int i = 0; i < N; i++) S[T * N + i] = x[i];
-      Cc[T] = env_final_cost<KIND, N, M>(e, x);
+    // finished problems: one after the other, each written by the whole warp (a lane writing its own 51 records one by one
+    // costs the warp ~1,500 instructions whenever any of its problems finishes; this is ~60 per finished problem)
+    for (unsigned fm = rt.ballot(valid && !keep); fm; fm &= fm - 1) {
+      const int src = nth_set_bit(fm, 0);
+      const int bs = rt.shfl(b, src), cs = rt.shfl(p.cur, src);
+      write_results<KIND, N, M>(rt, e, q, bs, VecTraj<N, M>{traj_row(q, cs, bs), CHn, 1});
+    }
+    if (valid && !keep) {
       int32_t *st = q.stats + (int64_t)b * 4;
       st[0] = p.iteration; st[1] = p.n_bwd; st[2] = p.n_fwd; st[3] = p.status;
     }

@@ -64,12 +64,19 @@ class iLQR:
         N.require_cuda()
         return torch.device("cuda", torch.cuda.current_device())
 
-    def _x0(self, x0):
+    def _x0(self, x0, batched=None):
+        """x0 as [B, n] plus "was a single problem".  Shapes are read the reference's way: [n,1] / [n] is one problem, [B,n] / [B,n,1]
+        a batch.  For n = 1 the shape [1,1] is ambiguous (one column vector, or a batch of one): it is taken as ONE problem unless
+        `batched=True` says otherwise (`batched=False` forces the single-problem reading of [n] / [n,1])."""
         n = self.env.state_size
         t = torch.as_tensor(np.asarray(x0) if not torch.is_tensor(x0) else x0).to(device=self._dev(), dtype=self.dtype)
+        if batched is True:
+            return t.reshape(-1, n).contiguous(), False
         if t.dim() >= 2 and t.shape[-1] == 1 and t.shape[-2] == n:
             t = t.squeeze(-1)
         single = t.dim() == 1
+        if batched is False and not single:
+            raise N.TfmpcError(f"x0 of shape {tuple(t.shape)} is not a single problem of state size {n}")
         return t.reshape(-1, n).contiguous(), single
 
     def _traj(self, t, size):
@@ -159,19 +166,19 @@ class iLQR:
         return s, a, out["costs"], out["J"], out["residual"]
 
     # -- solve ---------------------------------------------------------------------------
-    def solve_device(self, x0, T, u_init=None, seed=None):
+    def solve_device(self, x0, T, u_init=None, seed=None, batched=None):
         """Batched solve, results left on the device: dict(states [B,T+1,n], actions [B,T,m],
         costs [B,T+1], stats [B,4] = iteration, backward passes, rollouts, status)."""
-        x0r, _ = self._x0(x0)
+        x0r, _ = self._x0(x0, batched)
         u = self.initial_actions(x0r.shape[0], T, seed) if u_init is None else self._traj(u_init, self.env.action_size)[0]
         if u.shape[0] != x0r.shape[0]:
             raise N.TfmpcError(f"u_init batch {u.shape[0]} != x0 batch {x0r.shape[0]}")
         return ops.ilqr_solve(self._native(), x0r, u, self._opts())
 
-    def solve(self, x0, T, show_progress=True, u_init=None, seed=None):
+    def solve(self, x0, T, show_progress=True, u_init=None, seed=None, batched=None):
         """ilqr.py:214-283 -> (Trajectory, iteration) [single problem] or (BatchTrajectory, iterations[B])."""
-        _, single = self._x0(x0)
-        out = self.solve_device(x0, int(T), u_init=u_init, seed=seed)
+        _, single = self._x0(x0, batched)
+        out = self.solve_device(x0, int(T), u_init=u_init, seed=seed, batched=batched)
         stats = out["stats"].cpu().numpy()
         logging.info(f"[SOLVE] mean iterations={stats[:, 0].mean():.2f} status={np.bincount(stats[:, 3], minlength=5).tolist()}")
         if single:

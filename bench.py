@@ -394,6 +394,30 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def bind_to_gpu_numa_node(local):
+    """Multi-rank runs: keep this rank's host threads -- and, by first touch, its pinned staging buffers -- on the NUMA node its GPU
+    hangs off (what `numactl --cpunodebind --membind` per rank would do).  With 8 ranks moving 94 MB per step each, buffers that all
+    live on one socket put the whole end-to-end traffic on one memory controller and the inter-socket link.  Returns the node or None."""
+    try:
+        out = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(local)], capture_output=True, text=True,
+                             timeout=20).stdout.strip().splitlines()[0].strip().lower()
+        bdf = out[-12:] if len(out) >= 12 else out          # 00000000:1B:00.0 -> 0000:1b:00.0
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:  # noqa: BLE001 -- no topology information: leave the placement to the OS
+        return None
+
+
 def traffic_file(name):
     for rnd in ("r02", "r01"):
         path = os.path.join(ROOT, "profiles", f"{rnd}_traffic_{name}.json")
@@ -412,6 +436,7 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    numa_node = bind_to_gpu_numa_node(local) if world > 1 and not os.environ.get("TFMPC_BENCH_NO_NUMA") else None
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -692,7 +717,9 @@ def run_ours(args):
                              if per_rank else None),
                 "roofline": roofline,
                 "e2e": {"value": e2e_value, "unit": "problem-iterations/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                        "steps": e2e_steps, "host_threads": 1, "streams": S, "api": api},
+                        "steps": e2e_steps, "host_threads": 1, "streams": S, "api": api,
+                        "numa": (f"rank 0 bound to NUMA node {numa_node} (the node of its GPU; every rank does the same)" if numa_node is not None
+                                 else "not bound (single rank, or no topology information)")},
                 "gpu_launches": int(launches), "clocks": clocks, "extra": {}}
         if strong:
             line["extra"]["strong"] = strong
@@ -718,16 +745,18 @@ def extra_workloads(args):
     """Short runs of the other BASELINE configs, each in a process of its own (this file, --workload X), condensed to what the
     judge reads: value, roofline (frac, traffic), CPU baseline (cores, sample), end to end."""
     out = {}
-    for name, steps in (("c2", 20), ("c4", 3), ("c5s", 3), ("c5", 1)):
+    # (C4 / C5 single solve: 4 batches in flight -- the persistent kernel's last problems of one batch overlap the next batch, +20 %)
+    for name, steps, streams in (("c2", 20, 8), ("c4", 8, 4), ("c5s", 8, 4), ("c5", 1, 1)):
         cmd = [sys.executable, os.path.abspath(__file__), "--workload", name, "--steps", str(steps), "--warmup", "3", "--no-clock-sampler",
-               "--no-extra", "--streams", "1" if name != "c2" else "8"]
+               "--no-extra", "--streams", str(streams)]
         if args.no_cpu_baseline:
             cmd.append("--no-cpu-baseline")
         try:
             r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
             d = json.loads(r.stdout.strip().splitlines()[-1])
             out[name] = {"workload": d["config"]["workload"], "batch": d["config"]["global_batch"], "metric": d["metric"], "value": d["value"],
-                         "unit": d["unit"], "steps": d["steps"], "ms_per_step": d["ms_per_step"],
+                         "unit": d["unit"], "steps": d["steps"], "ms_per_step": d["ms_per_step"], "streams": d.get("details", {}).get("streams"),
+                         "sequential_latency_ms": (d.get("sequential") or {}).get("latency_ms_per_batch"),
                          "roofline": {k: d["roofline"].get(k) for k in ("bound", "achieved", "peak", "unit", "frac", "traffic", "kernel")},
                          "cpu_baseline": d.get("cpu_baseline"), "parity": d.get("parity"),
                          "e2e": {k: d["e2e"].get(k) for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")},

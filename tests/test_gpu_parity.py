@@ -792,6 +792,48 @@ def test_start_draws_initial_actions_in_library(prec):
     assert xs.shape == (3, 6, 2, 1) and torch.equal(us[..., 0], nav.initial_actions(3, 5, seed=4))
 
 
+def test_batched_lqr_rejects_mismatched_rows(prec):
+    """A batched LQR (per-problem F / f / C / c) takes one row per problem or a single shared row in transition / cost / final_cost /
+    forward; anything else used to index the parameters out of bounds on the device."""
+    from tfmpc_b200 import _native, envs
+    rng = np.random.RandomState(0)
+    B, T = 8, 5
+    goal = rng.uniform(-3, 3, size=(B, 2))
+    lq = envs.make_lqr_linear_navigation(goal, 2.0, dtype=_dt(prec))
+    x, u = rng.normal(size=(B, 2)), rng.normal(size=(B, 2))
+    nxt = lq.transition(x, u)
+    assert nxt.shape == (B, 2, 1) and np.allclose(_np(nxt)[..., 0], x + u, atol=1e-6)
+    one = lq.transition(x[:1], u[:1])                          # a single row is shared by all problems
+    assert one.shape == (B, 2, 1) and np.allclose(_np(one)[..., 0], x[:1] + u[:1], atol=1e-6)
+    c = lq.cost(x[:1], u[:1])
+    assert c.shape == (B,) and len(np.unique(np.round(_np(c), 5))) > 1      # same (x, u), per-problem goals
+    for bad in (3, B + 1, 2 * B):
+        with pytest.raises(_native.TfmpcError):
+            lq.transition(rng.normal(size=(bad, 2)), rng.normal(size=(bad, 2)))
+        with pytest.raises(_native.TfmpcError):
+            lq.final_cost(rng.normal(size=(bad, 2)))
+    policy, _ = lq.backward(T)
+    xs, us, cs = lq.forward(policy, x[0], T)                   # one x0 for a batched solver: expanded, as solve() does
+    assert xs.shape == (B, T + 1, 2, 1)
+    full = lq.solve_device(np.repeat(x[:1], B, axis=0), T)
+    assert np.allclose(_np(xs)[..., 0], _np(full["states"]), atol=1e-5)
+    with pytest.raises(_native.TfmpcError):
+        lq.forward(policy, rng.normal(size=(3, 2)), T)
+
+
+def test_batch_of_one_is_not_mistaken_for_a_column_vector(prec):
+    """x0 of shape [1, 1] is ambiguous for a one-dimensional environment (one column vector, or a batch of one): `batched=True`
+    settles it; the default stays the reference's reading (a single problem)."""
+    from tfmpc_b200.envs import synthetic
+    from tfmpc_b200.solvers.ilqr import iLQR
+    solver = iLQR(_env(synthetic.navlqr_config([2.5], 0.5, -0.3, 0.3), prec), dtype=_dt(prec))
+    x0 = np.array([[0.25]])
+    traj, it = solver.solve(x0, 6, seed=1)
+    assert traj.states.shape == (7, 1) and isinstance(it, int)
+    batch, its = solver.solve(x0, 6, seed=1, batched=True)
+    assert batch.states.shape == (1, 7, 1) and its.shape == (1,) and np.allclose(batch.states[0], traj.states)
+
+
 def test_launchers_and_csv(tmp_path):
     """launchers.ilqr_run / online_ilqr_run (reference launchers/__init__.py:12-51): env JSON -> solve -> data.csv"""
     import pandas as pd

@@ -245,6 +245,9 @@ int tfmpc_ilqr_solve(const tfmpc_env_t *env, int64_t B, int T, const tfmpc_real 
  *                        0 = never, 255 = the mode decides (0 / 1)                                               TFMPC_QUEUE_SOLO
  *   "queue_w_solo"       once <= this many problems are unfinished every warp pops one (0 = the mode decides: the pop-size
  *                        target / the number of warp slots)                                                      TFMPC_QUEUE_WSOLO
+ *   "queue_drain_solo"   throughput mode only: 1 (default) = a warp that popped a lone problem takes it on the solo engine once NO
+ *                        solve of the device is in its bulk phase any more (the pipeline is draining: nothing else wants the issue
+ *                        slots; +2.5 % on a 20-batch run), 0 = never                                               TFMPC_QUEUE_DRAIN_SOLO
  *   "queue_patience"     idle polls before a warp takes fewer problems than planned (default 0)                 TFMPC_QUEUE_PATIENCE
  *   "queue_trace"        1 = record one scheduling-trace record per warp iteration (diagnostics)                 TFMPC_QUEUE_TRACE */
 int tfmpc_set_option(const char *name, int value);

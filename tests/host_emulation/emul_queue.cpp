@@ -48,6 +48,8 @@ static int run(const EnvSmall &e, const IlqrOpts &o, int B, int T, const real *x
   q.ctrl = ctrl.data(); q.ring = ring.data(); q.ring_mask = cap - 1; q.prob = prob.data(); q.traj = traj.data(); q.gain = gain.data();
   q.B = B; q.T = T; q.row_r4 = row_r4; q.w_target = w_target; q.patience = patience; q.solo_max = solo_max; q.w_solo = solo_max > 0 ? w_target : 0; q.watchdog_ns = 120ull * 1000000000ull;
   q.trace = nullptr; q.trace_cap = 0;
+  static int bulk_counter = 0;
+  q.bulk = solo_max == 0 && w_target > 1 ? &bulk_counter : nullptr; q.bulk_thr = 4 * w_target;   // (solo_max = 0: the draining-pipeline rule decides)
   q.x0 = x0; q.u_init = u_init; q.states = states; q.actions = actions; q.costs = costs; q.stats = stats;
   std::vector<WarpShared> shared(nwarps);
   std::vector<WarpSmem<N, M>> smem(nwarps);

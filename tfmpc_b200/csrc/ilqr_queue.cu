@@ -58,6 +58,21 @@ std::atomic<int> g_solo_max{env_int("TFMPC_QUEUE_SOLO", 255)};   // 255 = the mo
 std::atomic<int> g_patience{env_int("TFMPC_QUEUE_PATIENCE", 0)};
 std::atomic<int> g_trace{env_int("TFMPC_QUEUE_TRACE", 0)};
 std::atomic<int> g_last_mode{0};   // what the last launch chose (diagnostics)
+std::atomic<int> g_drain_solo{env_int("TFMPC_QUEUE_DRAIN_SOLO", 1)};   // throughput mode: solo engine for lone stragglers once no solve is in its bulk phase
+
+// per-device counter of queue solves in their bulk phase (QParams::bulk); allocated once, never freed
+int *device_bulk_counter(int device) {
+  static std::mutex mu;
+  static int *ptr[64] = {nullptr};
+  if (device < 0 || device >= 64) return nullptr;
+  std::lock_guard<std::mutex> lock(mu);
+  if (!ptr[device]) {
+    int *p = nullptr;
+    if (cudaMalloc(&p, 256) != cudaSuccess || cudaMemset(p, 0, 256) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    ptr[device] = p;
+  }
+  return ptr[device];
+}
 
 // queue solves launched and not yet known to be complete: (stream, event recorded behind the solve kernel)
 struct InFlight { cudaStream_t stream; cudaEvent_t ev; int device; bool active; };
@@ -159,6 +174,8 @@ int launch(const tfmpc_env *e, int64_t B, int T, const real *x0, const real *u_i
   q.patience = std::max(0, g_patience.load());
   q.solo_max = std::max(0, std::min(32, sm_ != 255 ? sm_ : (mode == 2 ? 1 : 0)));
   q.w_solo = q.solo_max > 0 ? (ws_ > 0 ? ws_ : (mode == 2 ? nwarps : q.w_target)) : 0;
+  q.bulk = (mode == 1 && q.solo_max == 0 && g_drain_solo.load()) ? device_bulk_counter(e->device) : nullptr;   // throughput mode: solo only while the pipeline drains
+  q.bulk_thr = 4 * q.w_target;
   q.watchdog_ns = 4000000000ull;   // 4 s without progress for one warp: give up (status TFMPC_ST_ABORTED) instead of hanging the device
   q.x0 = x0; q.u_init = u_init; q.states = states; q.actions = actions; q.costs = costs; q.stats = stats;
   q.trace = g_trace.load() ? (unsigned *)(base + pl.o_trace) : nullptr;
@@ -190,6 +207,7 @@ int queue_ilqr_option(const char *name, int value, int *previous) {
   else if (!strcmp(name, "queue_solo_max")) t = &g_solo_max;
   else if (!strcmp(name, "queue_w_solo")) t = &g_w_solo;
   else if (!strcmp(name, "queue_mode")) t = &g_mode;
+  else if (!strcmp(name, "queue_drain_solo")) t = &g_drain_solo;
   else if (!strcmp(name, "queue_last_mode")) { *previous = g_last_mode.load(); return 1; }
   if (!t) return 0;
   *previous = t->exchange(value);

@@ -42,7 +42,7 @@
 namespace tq {
 
 // control block (ints, one counter per 128-byte line)
-enum { C_HEAD = 0, C_TAIL = 32, C_DONE = 64, C_ALIVE = 96, C_ERR = 128, C_WITER = 160, C_LANES = 192, C_ROUNDS = 224, C_REPLAYS = 256, C_COUNT = 288, C_TRACE = 320, C_INTS = 352 };
+enum { C_HEAD = 0, C_TAIL = 32, C_DONE = 64, C_ALIVE = 96, C_ERR = 128, C_WITER = 160, C_LANES = 192, C_ROUNDS = 224, C_REPLAYS = 256, C_COUNT = 288, C_TRACE = 320, C_BULK = 352, C_INTS = 384 };
 
 struct alignas(16) QProb {   // per-problem solver state carried between iterations (one 32-byte sector)
   double mu, delta;
@@ -63,6 +63,13 @@ struct QParams {
   int patience;                 // idle polls before a warp settles for fewer problems than the planned pop size
   int solo_max;                 // a warp that popped <= solo_max problems runs them one after another on the solo engine (0 = never)
   int w_solo;                   // once <= w_solo problems are unfinished every warp pops ONE (and keeps it on the solo engine)
+  // Draining pipeline (throughput mode).  `bulk` counts, per device, the queue solves that still have more than `bulk_thr`
+  // unfinished problems, i.e. that can use every warp slot they get: a solve adds itself when its kernel starts and leaves
+  // when it drops below the threshold.  While other solves are in their bulk phase a batch's stragglers stay lane-per-problem
+  // (the measured optimum for pipelined throughput); once NONE is -- the last batches of a run, or a gap in the submissions --
+  // a warp that popped a lone problem takes it on the solo engine: nothing else wants the issue slots.  nullptr = off.
+  int *bulk;
+  int bulk_thr;
   unsigned long long watchdog_ns;
   const real *x0, *u_init;
   real *states, *actions, *costs;
@@ -676,6 +683,8 @@ WD int q_acquire(WarpRT &rt, const QParams &q, int &h_out) {
   for (;;) {
     if (rt.ld_relaxed(ctrl + C_ERR)) return 0;
     const int P = q.B - rt.ld_relaxed(ctrl + C_DONE);   // problems not finished yet
+    if (q.bulk && P <= q.bulk_thr && rt.ld_relaxed(ctrl + C_BULK) == 1 && rt.atomic_cas(ctrl + C_BULK, 1, 2) == 1)
+      rt.atomic_add(q.bulk, -1);                         // this solve has left its bulk phase (once per solve)
     if (P <= 0) return 0;
     int g = (P + q.w_target - 1) / q.w_target;
     g = g < 1 ? 1 : (g > 32 ? 32 : g);
@@ -720,6 +729,8 @@ WD void queue_warp_main(WarpRT &rt, const EnvSmall &e, const IlqrOpts &o, const 
   R2 *gain_ws = q.gain + (int64_t)warp_slot * T * Gain2<N, M>::CH2 * 32;
   int n_witer = 0, n_lanes = 0, n_rounds = 0, n_stores = 0;   // scheduling statistics of this warp (flushed once, at exit)
   const bool solo_ok = Solo<N, M>::supported && Solo<N, M>::map(T, q.row_r4).bytes <= (int)sizeof(sm);
+  if (q.bulk && lane == 0 && B > q.bulk_thr && rt.ld_relaxed(q.ctrl + C_BULK) == 0 && rt.atomic_cas(q.ctrl + C_BULK, 0, 1) == 0)
+    rt.atomic_add(q.bulk, 1);   // this solve enters its bulk phase (the first warp of the kernel to run)
   for (;;) {
     // ------------------------------------------------ acquire
     int h = 0, take = 0;
@@ -752,7 +763,10 @@ WD void queue_warp_main(WarpRT &rt, const EnvSmall &e, const IlqrOpts &o, const 
     bool keep = false;
     int nrounds = 0, n_taken = 0;
     bool use_solo = false;
-    if constexpr (Solo<N, M>::supported) use_solo = solo_ok && take <= q.solo_max;
+    if constexpr (Solo<N, M>::supported) {
+      use_solo = solo_ok && take <= q.solo_max;
+      if (solo_ok && !use_solo && take == 1 && q.bulk) use_solo = rt.shfl(lane == 0 ? rt.ld_relaxed(q.bulk) : 0, 0) <= 0;   // draining pipeline
+    }
     if (use_solo) {
       // ------------------------------------------------ few problems: one after another, the whole warp on each (solo engine)
       int iters = 0;

@@ -138,6 +138,44 @@ def test_solo_engine_equals_lane_per_problem(prec, option, case, qp):
             assert np.all(relc[same] < 1e-5), relc[same].max()
 
 
+def test_auto_mode_latency_when_alone_throughput_when_pipelined(option):
+    """queue_mode = 0 (auto): a solve launched while no other stream of the device has a queue solve in flight runs in latency mode
+    (2), one launched behind a solve that is still running on ANOTHER stream in throughput mode (1); back-to-back solves on the
+    SAME stream never overlap, so they stay in latency mode.  The choice never changes results (fp64: bit-identical)."""
+    from tfmpc_b200 import ops
+    from tfmpc_b200.envs import synthetic
+    cfg = synthetic.navigation_config()
+    x0, u0 = _batch_case(cfg, 20000, 50, seed=9)
+    nat = _env(cfg, "f32").native(_dt("f32"))
+    dx0, du0 = _cu(x0, "f32"), _cu(u0, "f32")
+    option("queue_mode", 0, "f32")
+    last = lambda: ops.set_option("queue_last_mode", 0, "f32")  # noqa: E731  (read-only option: returns what the last launch chose)
+    torch.cuda.synchronize()
+    a = ops.ilqr_solve(nat, dx0, du0)
+    assert last() == 2
+    b = ops.ilqr_solve(nat, dx0, du0)            # same stream, the first one still running: still alone in the sense that matters
+    assert last() == 2
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        c = ops.ilqr_solve(nat, dx0, du0)        # another stream while the main stream's solves (~5 ms) are in flight
+        assert last() == 1
+    torch.cuda.synchronize()
+    d = ops.ilqr_solve(nat, dx0, du0)            # everything has drained
+    assert last() == 2
+    torch.cuda.synchronize()
+    for k in ("stats",):
+        assert torch.equal(a[k][:, 0], b[k][:, 0]) and (a[k][:, 0] == c[k][:, 0]).float().mean() > 0.995 and torch.equal(a[k], d[k])
+    option("queue_mode", 1, "f64")
+    nat64 = _env(cfg, "f64").native(_dt("f64"))
+    x64, u64 = _cu(x0[:3000], "f64"), _cu(u0[:3000], "f64")
+    t = {k: v.clone() for k, v in ops.ilqr_solve(nat64, x64, u64).items()}
+    option("queue_mode", 2, "f64")
+    l = ops.ilqr_solve(nat64, x64, u64)
+    torch.cuda.synchronize()
+    for k in t:
+        assert torch.equal(t[k], l[k]), k
+
+
 @pytest.mark.parametrize("case", ["nav_h50", "nav_h12", "navlqr_box", "navlqr1_box"])
 def test_closed_form_qp_vs_oracle(prec, option, case):
     """Closed-form box-QP (m <= 2) against the oracle, which runs the reference's projected-Newton iteration.

@@ -109,8 +109,7 @@ def test_solo_engine_equals_lane_per_problem(prec, option, case, qp):
     """The solo engine (a warp that popped <= queue_solo_max problems works on ONE problem with all its lanes: Q assembly
     spread over the lanes, candidates of all step sizes kept in shared memory, a lone problem kept until it has converged)
     evaluates the expressions of the lane-per-problem path in the same order.  queue_w_target above the batch size makes
-    every visit a solo visit.  fp64: identical results; fp32: separate compilations of the same expressions (FMA
-    contraction may differ), so the gate is agreement of the iteration counts on >= 99.5 %."""
+    every visit a solo visit.  Results are identical in both builds: the schedule never changes a problem's arithmetic."""
     from tfmpc_b200.envs import synthetic
     mk, B, T = CASES[case]
     cfg = mk(synthetic)
@@ -128,14 +127,10 @@ def test_solo_engine_equals_lane_per_problem(prec, option, case, qp):
         assert solo["counters"]["problem_iterations"] == int(solo["stats"][:, 1].sum()) or case == "navlqr_free"
         if solo_max == 32 or w_target >= B:      # every visit was a solo visit: one rollout round per iteration
             assert solo["counters"]["rounds"] == solo["counters"]["warp_iterations"]
-        same = solo["stats"][:, 0] == lanes["stats"][:, 0]
-        if prec == "f64":
-            for k in ("stats", "states", "actions", "costs"):
-                assert np.array_equal(solo[k], lanes[k]), (k, solo_max)
-        else:
-            assert same.mean() >= 0.995, same.mean()
-            relc = np.abs(solo["costs"].sum(1) - lanes["costs"].sum(1)) / np.maximum(np.abs(lanes["costs"].sum(1)), 1e-6)
-            assert np.all(relc[same] < 1e-5), relc[same].max()
+        # bit-identical in BOTH builds: fp64 is compiled without FMA contraction; in fp32 the only code that differs between the
+        # two shapes -- the Q assembly -- is written as explicit fma chains (r_fma), the rest is the same functions
+        for k in ("stats", "states", "actions", "costs"):
+            assert np.array_equal(solo[k], lanes[k]), (k, solo_max, float((solo["stats"][:, 0] == lanes["stats"][:, 0]).mean()))
 
 
 def test_auto_mode_latency_when_alone_throughput_when_pipelined(option):
@@ -150,12 +145,14 @@ def test_auto_mode_latency_when_alone_throughput_when_pipelined(option):
     dx0, du0 = _cu(x0, "f32"), _cu(u0, "f32")
     option("queue_mode", 0, "f32")
     last = lambda: ops.set_option("queue_last_mode", 0, "f32")  # noqa: E731  (read-only option: returns what the last launch chose)
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):                # warm the side stream's workspace: its allocation would synchronise the device later
+        ops.ilqr_solve(nat, dx0, du0)
     torch.cuda.synchronize()
     a = ops.ilqr_solve(nat, dx0, du0)
     assert last() == 2
     b = ops.ilqr_solve(nat, dx0, du0)            # same stream, the first one still running: still alone in the sense that matters
     assert last() == 2
-    side = torch.cuda.Stream()
     with torch.cuda.stream(side):
         c = ops.ilqr_solve(nat, dx0, du0)        # another stream while the main stream's solves (~5 ms) are in flight
         assert last() == 1
@@ -163,8 +160,8 @@ def test_auto_mode_latency_when_alone_throughput_when_pipelined(option):
     d = ops.ilqr_solve(nat, dx0, du0)            # everything has drained
     assert last() == 2
     torch.cuda.synchronize()
-    for k in ("stats",):
-        assert torch.equal(a[k][:, 0], b[k][:, 0]) and (a[k][:, 0] == c[k][:, 0]).float().mean() > 0.995 and torch.equal(a[k], d[k])
+    for k in ("stats", "states", "actions", "costs"):       # latency or throughput mode, solo engine or not: same results, bit for bit
+        assert torch.equal(a[k], b[k]) and torch.equal(a[k], c[k]) and torch.equal(a[k], d[k]), k
     option("queue_mode", 1, "f64")
     nat64 = _env(cfg, "f64").native(_dt("f64"))
     x64, u64 = _cu(x0[:3000], "f64"), _cu(u0[:3000], "f64")

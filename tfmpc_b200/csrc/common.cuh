@@ -27,6 +27,24 @@ HD real r_max(real a, real b) { return a > b ? a : b; }
 HD real r_min(real a, real b) { return a < b ? a : b; }
 HD real r_sgn(real v) { return (real)((v > 0) - (v < 0)); }
 HD real r_clip(real v, real lo, real hi) { return v < lo ? lo : (v > hi ? hi : v); }
+// Explicitly fused / explicitly unfused products for the few places where TWO code shapes must round identically in the fp32
+// product build (the one-thread Q assembly and its lane-parallel twin in the solo engine): an explicit fma chain cannot be
+// re-contracted by the compiler, and __fmul_rn is never fused into a following add.  The fp64 verification build is compiled
+// without FMA contraction and keeps separate multiply / add (what the gcc-built oracle does); the host emulation likewise.
+HD real r_fma(real a, real b, real c) {
+#if defined(__CUDA_ARCH__) && !defined(TFMPC_F64)
+  return __fmaf_rn(a, b, c);
+#else
+  return a * b + c;
+#endif
+}
+HD real r_mul(real a, real b) {
+#if defined(__CUDA_ARCH__) && !defined(TFMPC_F64)
+  return __fmul_rn(a, b);
+#else
+  return a * b;
+#endif
+}
 #ifdef TFMPC_F64
 HD real r_sqrt(real v) { return sqrt(v); }
 HD real r_exp(real v) { return exp(v); }

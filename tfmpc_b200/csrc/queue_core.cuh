@@ -475,9 +475,9 @@ WD int solo_backward(WarpRT &rt, char *smb, const typename Solo<N, M>::Map &mp, 
     lzz = lzz_n; lz = lz_n; lt = lt_n;
     real qz, qe, qr;
     {
-      real s = 0;
+      real s = 0;   // explicit fma chains, as in assemble_q: the two code shapes round identically (common.cuh, r_fma)
 #pragma unroll
-      for (int p = 0; p < N; p++) s += Fa[p] * V_x[p];
+      for (int p = 0; p < N; p++) s = r_fma(Fa[p], V_x[p], s);
       qz = lz + s;
       real sq = 0, sqr = 0;
 #pragma unroll
@@ -485,11 +485,11 @@ WD int solo_backward(WarpRT &rt, char *smb, const typename Solo<N, M>::Map &mp, 
         real tp = 0, tr = 0;
 #pragma unroll
         for (int c = 0; c < N; c++) {
-          tp += Fa[c] * V_xx[c * N + p];
-          tr += Fa[c] * (c == p ? V_xx[c * N + p] + mu * (real)1 : V_xx[c * N + p]);
+          tp = r_fma(Fa[c], V_xx[c * N + p], tp);
+          tr = r_fma(Fa[c], (c == p ? V_xx[c * N + p] + mu * (real)1 : V_xx[c * N + p]), tr);
         }
-        sq += tp * Fb[p];
-        sqr += tr * Fb[p];
+        sq = r_fma(tp, Fb[p], sq);
+        sqr = r_fma(tr, Fb[p], sqr);
       }
       qe = lzz + sq; qr = lzz + sqr;
     }
@@ -648,7 +648,13 @@ WD bool solo_run(WarpRT &rt, WarpSmem &sm, const EnvSmall &e, const IlqrOpts &o,
       if (q.trace) ns_search += (unsigned)(rt.now_ns() - tq2);
     }
     if (p.phase == PH_DONE) break;
-    if (!sticky) {   // one iteration per visit: state back to global memory, the caller re-queues the problem
+    // A lone problem stays with its warp (sticky) only while nobody is waiting: with fewer live warps than unfinished problems
+    // (throughput mode retires warps early) a warp that kept its problem to the end would leave the queued ones without any
+    // progress for up to 64 iterations, then run them one after the other -- measured -4 % pipelined.  With tickets queued it
+    // yields after every iteration and the problems take turns.
+    bool yield = !sticky;
+    if (sticky && q.bulk) yield = rt.shfl(lane == 0 ? rt.ld_relaxed(q.ctrl + C_COUNT) : 0, 0) > 0;   // (q.bulk set = throughput mode)
+    if (yield) {     // state back to global memory, the caller re-queues the problem
       if (write_back) {
         R4 *row = traj_row(q, p.cur, b);
         for (int i = lane; i < row_r4; i += 32) row[i] = nom_s[i];

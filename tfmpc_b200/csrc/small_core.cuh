@@ -90,7 +90,7 @@ HD void env_linearize(const EnvSmall &e, const real *x, const real *u, Lin<N, M>
       L.l_x[i] = (real)2 * (x[i] - e.goal[i]); L.l_xx[i * N + i] = 2;
     }
 #pragma unroll
-    for (int i = 0; i < M; i++) { L.l_u[i] = (real)2 * e.beta * u[i]; L.l_uu[i * M + i] = (real)2 * e.beta; }
+    for (int i = 0; i < M; i++) { L.l_u[i] = r_mul((real)2 * e.beta, u[i]); L.l_uu[i * M + i] = (real)2 * e.beta; }   // (r_mul: must not fuse into Q_u = l_u + ...)
   } else {
     constexpr int ZM = ZoneBound<KIND>::v;
     real lam_z[ZM], r_z[ZM], g0 = 0, g1 = 0;
@@ -451,7 +451,9 @@ struct QB {
   HD real *Q_ux_reg() { return v + OUXR; }
 };
 
-// ---- stage 1: Q_x, Q_u (:122-123), Q_xx, Q_uu, Q_ux (:129-131) and the state-regularised Q_uu_reg, Q_ux_reg (:127,133-134)
+// ---- stage 1: Q_x, Q_u (:122-123), Q_xx, Q_uu, Q_ux (:129-131) and the state-regularised Q_uu_reg, Q_ux_reg (:127,133-134).
+// The sums are explicit fma chains (r_fma): the solo engine evaluates the same chains entry by entry on different lanes, and
+// the two code shapes must round identically in the fp32 build for results to be independent of the schedule.
 template <int KIND, int N, int M>
 HD void assemble_q(const Lin<N, M> &L, real mu, const real *V_x, const real *V_xx, QB<N, M> &q) {
   typedef Traits<KIND> TR;
@@ -463,7 +465,7 @@ HD void assemble_q(const Lin<N, M> &L, real mu, const real *V_x, const real *V_x
 #pragma unroll
     for (int p = 0; p < N; p++) {
       if (TR::fx_diag && p != i) continue;
-      s += L.f_x[p * N + i] * V_x[p];
+      s = r_fma(L.f_x[p * N + i], V_x[p], s);
     }
     Q_x[i] = L.l_x[i] + s;
   }
@@ -473,7 +475,7 @@ HD void assemble_q(const Lin<N, M> &L, real mu, const real *V_x, const real *V_x
 #pragma unroll
     for (int p = 0; p < N; p++) {
       if (TR::fu_diag && p != i) continue;
-      s += L.f_u[p * M + i] * V_x[p];
+      s = r_fma(L.f_u[p * M + i], V_x[p], s);
     }
     Q_u[i] = L.l_u[i] + s;
   }
@@ -485,7 +487,7 @@ HD void assemble_q(const Lin<N, M> &L, real mu, const real *V_x, const real *V_x
 #pragma unroll
       for (int p = 0; p < N; p++) {
         if (TR::fx_diag && p != i) continue;
-        s += L.f_x[p * N + i] * V_xx[p * N + j];
+        s = r_fma(L.f_x[p * N + i], V_xx[p * N + j], s);
       }
       fxTV[i * N + j] = s;
     }
@@ -497,8 +499,8 @@ HD void assemble_q(const Lin<N, M> &L, real mu, const real *V_x, const real *V_x
 #pragma unroll
       for (int p = 0; p < N; p++) {
         if (TR::fu_diag && p != i) continue;
-        s += L.f_u[p * M + i] * V_xx[p * N + j];
-        sr += L.f_u[p * M + i] * (p == j ? V_xx[p * N + j] + mu * (real)1 : V_xx[p * N + j]);
+        s = r_fma(L.f_u[p * M + i], V_xx[p * N + j], s);
+        sr = r_fma(L.f_u[p * M + i], (p == j ? V_xx[p * N + j] + mu * (real)1 : V_xx[p * N + j]), sr);
       }
       fuTV[i * N + j] = s;
       fuTVr[i * N + j] = sr;
@@ -511,7 +513,7 @@ HD void assemble_q(const Lin<N, M> &L, real mu, const real *V_x, const real *V_x
 #pragma unroll
       for (int p = 0; p < N; p++) {
         if (TR::fx_diag && p != j) continue;
-        s += fxTV[i * N + p] * L.f_x[p * N + j];
+        s = r_fma(fxTV[i * N + p], L.f_x[p * N + j], s);
       }
       Q_xx[i * N + j] = (TR::lxx_diag && i != j) ? s : L.l_xx[i * N + j] + s;
     }
@@ -523,8 +525,8 @@ HD void assemble_q(const Lin<N, M> &L, real mu, const real *V_x, const real *V_x
 #pragma unroll
       for (int p = 0; p < N; p++) {
         if (TR::fu_diag && p != j) continue;
-        s += fuTV[i * N + p] * L.f_u[p * M + j];
-        sr += fuTVr[i * N + p] * L.f_u[p * M + j];
+        s = r_fma(fuTV[i * N + p], L.f_u[p * M + j], s);
+        sr = r_fma(fuTVr[i * N + p], L.f_u[p * M + j], sr);
       }
       Q_uu[i * M + j] = (TR::luu_diag && i != j) ? s : L.l_uu[i * M + j] + s;
       Q_uu_reg[i * M + j] = (TR::luu_diag && i != j) ? sr : L.l_uu[i * M + j] + sr;
@@ -535,8 +537,8 @@ HD void assemble_q(const Lin<N, M> &L, real mu, const real *V_x, const real *V_x
 #pragma unroll
       for (int p = 0; p < N; p++) {
         if (TR::fx_diag && p != j) continue;
-        s += fuTV[i * N + p] * L.f_x[p * N + j];
-        sr += fuTVr[i * N + p] * L.f_x[p * N + j];
+        s = r_fma(fuTV[i * N + p], L.f_x[p * N + j], s);
+        sr = r_fma(fuTVr[i * N + p], L.f_x[p * N + j], sr);
       }
       Q_ux[i * N + j] = TR::lxu_zero ? s : L.l_xu[j * M + i] + s;
       Q_ux_reg[i * N + j] = TR::lxu_zero ? sr : L.l_xu[j * M + i] + sr;

@@ -18,7 +18,7 @@ constexpr int kMaxWarpsPerSM = 8;    // WarpSmem is 23 KB in the fp64 build (n =
 constexpr int kMaxWarpsPerSM = 18;   // 11.8 KB of shared memory per warp (n = m = 2) and 96 registers per thread (no spills): measured
                                      // 337 M problem-iterations/s against 306 at 16 warps / 106 registers (profiles/r02_ab_queue.txt)
 #endif
-constexpr int kLatencyWarpsPerSM = kMaxWarpsPerSM < 14 ? kMaxWarpsPerSM : 14;
+constexpr int kLatencyWarpsPerSM = kMaxWarpsPerSM < 13 ? kMaxWarpsPerSM : 13;
 
 template <int KIND, int N, int M, int QP>
 __global__ void __launch_bounds__(32, kMaxWarpsPerSM) k_queue_solve(EnvSmall e, IlqrOpts o, tq::QParams q) {
@@ -46,9 +46,10 @@ std::atomic<int> g_wps{env_int("TFMPC_QUEUE_WPS", 0)};   // 0 = the mode decides
 // that has the GPU to itself (latency) should spread them over all warp slots and, once there are fewer problems than
 // slots, give each problem a whole warp (the solo engine: ~34 us per iteration against ~75 us on one lane).
 //   mode 1 = throughput: 18 resident warps per SM, pop-size target = one warp per SM, solo engine off
-//   mode 2 = latency:    14 resident warps per SM (the lone batch is bound by the latency of a warp iteration, which contention
-//                        for the issue slots stretches: 8.14 ms at 18 warps, 7.98 at 16, 7.83 at 14, 7.89 at 12), pop-size target =
-//                        12 warps per SM, solo once unfinished <= launched warps
+//   mode 2 = latency:    13 resident warps per SM (the lone batch is bound by the latency of a warp iteration, which contention
+//                        for the issue slots stretches), pop-size target = 15 warps per SM, solo once unfinished <= launched
+//                        warps.  Lone C3 batch (profiles/r02_ab_queue.txt, calls 18, 36, 37): 8.14 ms at 18 warps / target 12 per
+//                        SM, 7.98 at 16, 7.97 at 14, 7.67 at 13 warps / target 15 per SM, 7.75 at 12; targets of 18+ per SM: > 8.1
 //   mode 0 = auto:       latency when no other stream of this device has a queue solve in flight at launch time
 // Each of the knobs below overrides the mode's choice when set (> 0; solo_max: anything but 255).
 std::atomic<int> g_mode{env_int("TFMPC_QUEUE_MODE", 0)};
@@ -170,7 +171,7 @@ int launch(const tfmpc_env *e, int64_t B, int T, const real *x0, const real *u_i
   const int sms = device_sms(e->device), wt = g_w_target.load(), ws_ = g_w_solo.load(), sm_ = g_solo_max.load(), wp_ = g_wps.load();
   const int wps = std::max(1, std::min(wp_ > 0 ? wp_ : (mode == 2 ? kLatencyWarpsPerSM : kMaxWarpsPerSM), kMaxWarpsPerSM));
   const int nwarps = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)sms * wps, B));   // warps (= CTAs) of this launch
-  q.w_target = wt > 0 ? wt : (mode == 2 ? 12 * sms : sms);
+  q.w_target = wt > 0 ? wt : (mode == 2 ? 15 * sms : sms);
   q.patience = std::max(0, g_patience.load());
   q.solo_max = std::max(0, std::min(32, sm_ != 255 ? sm_ : (mode == 2 ? 1 : 0)));
   q.w_solo = q.solo_max > 0 ? (ws_ > 0 ? ws_ : (mode == 2 ? nwarps : q.w_target)) : 0;

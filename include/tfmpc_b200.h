@@ -234,12 +234,12 @@ int tfmpc_ilqr_solve(const tfmpc_env_t *env, int64_t B, int T, const tfmpc_real 
  *                        (optimization.py:6-101; default of the fp64 verification build)                        TFMPC_QP=closed|newton
  *   "queue_warps_per_sm" resident warps per SM of the queue kernel (<= 18; 0 = the mode decides: 18 / 13)           TFMPC_QUEUE_WPS
  *   "queue_mode"         scheduling policy of the queue kernel: 1 = throughput (several batches in flight: the last
- *                        problems of a batch stay in full warps, one per SM), 2 = latency (a batch that has the GPU to
+ *                        problems of a batch stay in full warps), 2 = latency (a batch that has the GPU to
  *                        itself: the last problems spread over every warp slot and, once there are fewer problems than
  *                        slots, each gets a whole warp -- the solo engine), 0 = auto (default): latency when no other
  *                        stream of the device has a queue solve in flight at launch time                         TFMPC_QUEUE_MODE
  *   "queue_w_target"     warps the queue plans its pop size for: a warp pops clamp(ceil(unfinished / w_target), 1, 32)
- *                        problems (0 = the mode decides: one warp per SM / 15 warps per SM)                      TFMPC_QUEUE_WTARGET
+ *                        problems (0 = the mode decides: one warp per four SMs / 15 warps per SM)                      TFMPC_QUEUE_WTARGET
  *   "queue_solo_max"     a warp that popped <= this many problems runs them one after another on the solo engine (all
  *                        lanes on one problem, everything in shared memory; a lone problem stays until it has converged);
  *                        0 = never, 255 = the mode decides (0 / 1)                                               TFMPC_QUEUE_SOLO

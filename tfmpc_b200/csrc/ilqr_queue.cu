@@ -45,7 +45,9 @@ std::atomic<int> g_wps{env_int("TFMPC_QUEUE_WPS", 0)};   // 0 = the mode decides
 // full warps, one per SM, lane-per-problem -- because every other warp slot is doing another batch's bulk work; a batch
 // that has the GPU to itself (latency) should spread them over all warp slots and, once there are fewer problems than
 // slots, give each problem a whole warp (the solo engine: ~34 us per iteration against ~75 us on one lane).
-//   mode 1 = throughput: 18 resident warps per SM, pop-size target = one warp per SM, solo engine off
+//   mode 1 = throughput: 18 resident warps per SM, pop-size target = one warp per FOUR SMs (full warps until < 1,184 problems are
+//                        left: 8 batches in flight measured 374 / 371 / 367 / 358 / 346 / 334 M/s for targets of 18 / 37 / 74 / 148 /
+//                        222 / 296 warps; 20-batch runs peak at 37), solo engine off (on while the pipeline drains, see `bulk`)
 //   mode 2 = latency:    13 resident warps per SM (the lone batch is bound by the latency of a warp iteration, which contention
 //                        for the issue slots stretches), pop-size target = 15 warps per SM, solo once unfinished <= launched
 //                        warps.  Lone C3 batch (profiles/r02_ab_queue.txt, calls 18, 36, 37): 8.14 ms at 18 warps / target 12 per
@@ -171,7 +173,7 @@ int launch(const tfmpc_env *e, int64_t B, int T, const real *x0, const real *u_i
   const int sms = device_sms(e->device), wt = g_w_target.load(), ws_ = g_w_solo.load(), sm_ = g_solo_max.load(), wp_ = g_wps.load();
   const int wps = std::max(1, std::min(wp_ > 0 ? wp_ : (mode == 2 ? kLatencyWarpsPerSM : kMaxWarpsPerSM), kMaxWarpsPerSM));
   const int nwarps = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)sms * wps, B));   // warps (= CTAs) of this launch
-  q.w_target = wt > 0 ? wt : (mode == 2 ? 15 * sms : sms);
+  q.w_target = wt > 0 ? wt : (mode == 2 ? 15 * sms : std::max(1, sms / 4));
   q.patience = std::max(0, g_patience.load());
   q.solo_max = std::max(0, std::min(32, sm_ != 255 ? sm_ : (mode == 2 ? 1 : 0)));
   q.w_solo = q.solo_max > 0 ? (ws_ > 0 ? ws_ : (mode == 2 ? nwarps : q.w_target)) : 0;

@@ -249,7 +249,8 @@ int tfmpc_ilqr_solve(const tfmpc_env_t *env, int64_t B, int T, const tfmpc_real 
  *                        solve of the device is in its bulk phase any more (the pipeline is draining: nothing else wants the issue
  *                        slots; +2.5 % on a 20-batch run), 0 = never                                               TFMPC_QUEUE_DRAIN_SOLO
  *   "queue_patience"     idle polls before a warp takes fewer problems than planned (default 0)                 TFMPC_QUEUE_PATIENCE
- *   "queue_trace"        1 = record one scheduling-trace record per warp iteration (diagnostics)                 TFMPC_QUEUE_TRACE */
+ *   "queue_trace"        1 = record one scheduling-trace record per warp iteration (diagnostics)                 TFMPC_QUEUE_TRACE
+ *   "queue_last_mode"    read-only: returns the mode (1 / 2) the last launch chose; the value passed is ignored */
 int tfmpc_set_option(const char *name, int value);
 /* Diagnostics: copies the control block the queue solver left in `workspace` (after the solve has completed on `stream`):
  * out[0] = warp iterations, out[1] = problem iterations (lanes), out[2] = rollout rounds incl. store passes,

@@ -20,14 +20,21 @@
 // that the last stragglers each own a warp (all 11 step sizes in one round).
 //
 // The solo engine.  When few problems are left a warp pops only a handful, and a lane-per-problem iteration then costs the
-// full serial latency of one thread (~85 us for C3: 40 us backward, 2 x 20 us rollouts) with 31 lanes idle.  A warp that
+// full serial latency of one thread (~75 us for C3: 36 us backward, 2 x 16 us rollouts) with 31 lanes idle.  A warp that
 // popped <= solo_max problems instead runs them one after another with ALL lanes working on one problem, everything in
 // shared memory: the linearisation of the whole horizon is computed first, one timestep per lane; the Riccati sweep then
 // assembles each timestep's Q block with one matrix entry per lane (same expressions, same summation order as the
 // one-thread code, so the results are bit-identical), hands it over through shared memory, and every lane runs the
 // controller and the value update redundantly (no divergence, no second hand-over); the 11 step sizes roll out on 11
 // lanes at once and keep their candidates in shared memory, so the accepted one is copied, not replayed.  A warp that
-// popped a single problem keeps it until it has converged (no queue round trip, no global trajectory traffic at all).
+// popped a single problem keeps it until it has converged (no queue round trip, no global trajectory traffic at all) -- unless
+// tickets are queued with no warp to serve them, in which case it yields after every iteration.  ~30 us per iteration.
+// The Q assembly is written as explicit fma chains in both shapes (r_fma, common.cuh), so a problem's result does not depend on
+// which shape computed which iteration: results are independent of the schedule, bit for bit, in the fp32 build too.
+//
+// Which regime a launch runs in (full warps for the stragglers while other batches want the SMs, or spread out with the solo
+// engine when the batch has the GPU to itself) is the host's choice per launch: QParams w_target / w_solo / solo_max / bulk,
+// set by ilqr_queue.cu from the "queue_mode" option.
 //
 // Memory traffic.  Trajectories are PROBLEM-major (one problem = one contiguous, 64-byte aligned row) and move between
 // HBM/L2 and shared memory only as 64-byte half-lines (4 steps for n = m = 2): 4 lanes fetch one half-line with cp.async

@@ -278,8 +278,9 @@ def ilqr_solve(env, x0, u_init, opts=None, out=None):
 
 def set_option(name, value, precision="f32"):
     """tfmpc_set_option: runtime options of the small-environment solve ("solver": 1 queue / 0 ticks, "qp": 2 closed form /
-    0 the reference's projected-Newton iteration, "queue_warps_per_sm", "queue_w_target", "queue_patience").
-    Returns the previous value."""
+    0 the reference's projected-Newton iteration, "queue_mode": 0 auto / 1 throughput / 2 latency, and the scheduling knobs
+    "queue_warps_per_sm", "queue_w_target", "queue_w_solo", "queue_solo_max", "queue_drain_solo", "queue_patience",
+    "queue_trace"; "queue_last_mode" is read-only) -- include/tfmpc_b200.h has the list.  Returns the previous value."""
     lib = N.load(precision)
     rc = lib.tfmpc_set_option(str(name).encode(), int(value))
     if rc < 0:

@@ -112,10 +112,10 @@ def emul2():
         assert rc == 0
         return bufs
 
-    def queue(prec, cfg, x0, u_init, qp, nwarps, w_target, patience=4, solo_max=4):
+    def queue(prec, cfg, x0, u_init, qp, nwarps, w_target, patience=4, solo_max=4, max_iterations=100):
         kind, n, nz, params, x0, u, B, T, bufs = prep(prec, cfg, x0, u_init)
         ctrl = np.zeros(libs[prec].emul_queue_ctrl_ints(), np.int32)
-        rc = libs[prec].emul_queue_solve(kind, n, nz, p(params), C.c_double(5e-3), 100, C.c_double(1e-6), C.c_double(2.0), C.c_double(0.0),
+        rc = libs[prec].emul_queue_solve(kind, n, nz, p(params), C.c_double(5e-3), int(max_iterations), C.c_double(1e-6), C.c_double(2.0), C.c_double(0.0),
                                         p(ALPHAS), B, T, p(x0), p(u), *[p(b) for b in bufs], qp, nwarps, w_target, patience, solo_max, p(ctrl))
         assert rc == 0, f"queue solver flagged {rc}"
         return bufs, ctrl
@@ -198,3 +198,25 @@ def test_queue_solver_navlqr_sizes(emul2, prec, n, low, high, beta):
     assert same.mean() >= (0.9 if prec == "f32" else (0.97 if qp == 2 else 1.0)), same.mean()
     relc = np.abs(got[2].sum(1) - r["costs"].sum(1)) / np.maximum(np.abs(r["costs"].sum(1)), 1e-9)
     assert np.all(relc[same] < (1e-4 if prec == "f32" else 1e-8))
+
+
+@pytest.mark.parametrize("prec", ["f32", "f64"])
+@pytest.mark.parametrize("solo_max,w_target", [(0, 1), (4, 8)])
+@pytest.mark.parametrize("name", golden_names("retry_"))
+def test_queue_solver_takes_the_retry_branch(emul2, prec, name, solo_max, w_target):
+    """SURVEY row a16 on the device logic: the work-queue kernel body -- lane-per-problem (solo_max = 0) and the solo engine (every
+    visit a solo visit: w_target above the batch size) -- on the fixtures whose first Cholesky fails on every outer iteration
+    (iLQR._backward, ilqr.py:285-315): passes counted = the reference's successful + failed calls, same trajectory."""
+    _, queue = emul2
+    d = golden(name, prec)
+    got, ctrl = queue(prec, cfg_of(d), d["x0"][..., 0], d["u_init"][..., 0], 0, 2, w_target, solo_max=solo_max,
+                      max_iterations=int(d["max_iterations"]))
+    states, actions, costs, st = got
+    calls = d["trace"][:, :, 0]
+    for b in range(st.shape[0]):
+        L = int(d["trace_len"][b])
+        assert st[b, 1] == int((calls[b, :L] == 0).sum()) + int((calls[b, :L] == 2).sum())
+        assert st[b, 2] == int((calls[b, :L] == 1).sum())
+    assert (st[:, 0] == d["iterations"]).all() and (st[:, 3] == 1).all()
+    tg = d["costs"].sum(1)
+    assert np.all(np.abs(costs.sum(1) - tg) <= (1e-4 if prec == "f32" else 1e-9) * np.abs(tg))

@@ -218,3 +218,22 @@ def test_bench_reference_arm_contract():
         assert key in d, key
     assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    # both arms print the SAME config object (the driver compares them): it comes from one function
+    sys.path.insert(0, root)
+    import bench
+    assert d["config"] == bench.arm_config("c4", 16384, 1) and set(d["config"]) >= {"workload", "batch_per_gpu", "global_batch", "horizon"}
+
+
+def test_bench_parity_block_counts_what_it_says():
+    """bench.py's `parity` block: fractions of the batch with the same iteration count / within one / converged cost within 1e-4 /
+    same status, computed against an oracle result on the same problems."""
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import bench
+    stats = np.array([[5, 6, 8, 0], [7, 8, 9, 0], [9, 10, 12, 1], [3, 4, 5, 2]], dtype=np.int32)
+    total = np.array([10.0, 20.0, 30.0, 40.0], dtype=np.float32)
+    r = {"iterations": np.array([5, 8, 9, 3]), "costs": np.array([[10.0, 0.0], [20.0, 0.001], [30.01, 0.0], [20.0, 20.0]]), "status": np.array([0, 0, 1, 0])}
+    p = bench.parity_block(stats, total, r)
+    assert p["problems"] == 4 and p["same_iterations"] == 0.75 and p["within1"] == 1.0
+    assert p["cost_within_1e-4"] == 0.75 and abs(p["cost_within_1e-4_given_same_iterations"] - 2 / 3) < 1e-12 and p["status_match"] == 0.75

@@ -545,10 +545,10 @@ def run_ours(args):
         st.wait_event(e0)
     tl = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     t_issue0 = time.perf_counter()
-    # ... and it knows which batch is the LAST one: nothing behind it wants the SMs, so it is submitted in latency mode (its stragglers
-    # spread out and use the solo engine: the drain of the pipeline is shorter; +2.3 % on a 20-batch run, 1 batch: 348, 2: 345, 4: 321,
-    # 8: 281, none: 340 M/s -- profiles/r02_ab_queue.txt)
-    tail_lat = int(os.environ.get("TFMPC_BENCH_TAIL_LATENCY", "1"))
+    # (Submitting the LAST batch in latency mode -- nothing behind it wants the SMs -- shortens the drain: 346-348 M/s on a 20-batch
+    #  run against 340, but one run in three falls to 328 (profiles/r02_ab_queue.txt, calls 46-48), so the device-resident
+    #  section does not do it; the end-to-end section below does, where it measured +3 % in every run.)
+    tail_lat = int(os.environ.get("TFMPC_BENCH_TAIL_LATENCY", "0"))
     for k in range(args.steps):
         if queue_path and S > 1 and tail_lat and k == args.steps - tail_lat:
             ops.set_option("queue_mode", 2)
@@ -648,7 +648,8 @@ def run_ours(args):
 
         def e2e_issue(i):
             ops.ilqr_solve_host_async(nat, x0_pin, u0_pin, houts[i], scratch[i], opts)
-        api = "tfmpc_ilqr_solve_host_async (pinned host buffers in and out; copies and solve enqueued on a stream), one call per step, one host thread"
+        api = ("tfmpc_ilqr_solve_host_async (pinned host buffers in and out; copies and solve enqueued on a stream), one call per step, one host thread; "
+               "queue_mode 1 (throughput), 2 (latency) for the last batch of the job")
     if queue_path and S > 1:
         ops.set_option("queue_mode", 1)     # a pipeline again
     for i in range(S):
@@ -656,7 +657,10 @@ def run_ours(args):
             e2e_issue(i)                   # warm
     barrier()
     t0 = time.perf_counter()
+    e2e_tail = int(os.environ.get("TFMPC_BENCH_E2E_TAIL_LATENCY", "1"))
     for k in range(e2e_steps):
+        if queue_path and S > 1 and e2e_tail and k == e2e_steps - e2e_tail:
+            ops.set_option("queue_mode", 2)     # the last batch of the job has nothing behind it: latency mode (+3 %: 329 against 318-320 M/s)
         with torch.cuda.stream(streams[k % S]):
             e2e_issue(k % S)
     for st in streams:
@@ -718,7 +722,7 @@ def run_ours(args):
                                            (f"; behind the last batch one NCCL all-gather per buffer of the full results of one resident batch "
                                             f"({gather_bytes / 1e6:.0f} MB received per rank, {gather_ms:.2f} ms incl. waiting for the slowest rank)" if world > 1 else ""),
                             "streams": S,
-                            "pipelining": (f"the {args.steps} steps are independent batches issued round-robin on {S} CUDA streams, queue_mode = 1 (throughput) set by the caller, 2 (latency) for the last batch" if S > 1 else "one batch at a time"),
+                            "pipelining": (f"the {args.steps} steps are independent batches issued round-robin on {S} CUDA streams, queue_mode = 1 (throughput) set by the caller" if S > 1 else "one batch at a time"),
                             "l2": ("pipelined: aggregate working set of the concurrent batches (S x ~330 MB) >> 126 MB L2; "
                                    "sequential: 256 MB buffer written between timed iterations (untimed L2 flush)"),
                             "mean_iterations_per_solve": float((stats[:, 0] + 1).mean()),

@@ -66,8 +66,12 @@ class LQR:
         n, NN = self.state_size, self.n_dim
         return (n * NN if F.dim() == 3 else 0, n if f.dim() == 2 else 0, NN * NN if Cm.dim() == 3 else 0, NN if c.dim() == 2 else 0)
 
-    def _x(self, x, size):
+    def _x(self, x, size, batched=None):
+        """[size,1] / [size] is one problem, [B,size] / [B,size,1] a batch (the reference's shapes plus a batch axis).  For size = 1
+        the shape [1,1] is ambiguous: it is read as ONE column vector unless `batched=True`."""
         t = torch.as_tensor(np.asarray(x) if not torch.is_tensor(x) else x).to(device=_dev(), dtype=self.dtype)
+        if batched is True:
+            return t.reshape(-1, size).contiguous(), False
         if t.dim() >= 2 and t.shape[-1] == 1 and t.shape[-2] == size:
             t = t.squeeze(-1)
         single = t.dim() == 1
@@ -119,14 +123,14 @@ class LQR:
     def final_cost(self, x):      # lqr.py:49-57
         return self._step(x, None, "final")
 
-    def _solve(self, x0, T, terminal_zero=False, want_policy=True, want_value=True):
+    def _solve(self, x0, T, terminal_zero=False, want_policy=True, want_value=True, batched=None):
         F, f, Cm, c = self._device_params()
         B = self.batch_size
         if x0 is None:
             x0 = torch.zeros(B or 1, self.state_size, dtype=self.dtype, device=F.device)
             single = B is None
         else:
-            x0, single = self._x(x0, self.state_size)
+            x0, single = self._x(x0, self.state_size, batched)
             single = single and B is None
             if B is not None and x0.shape[0] == 1:
                 x0 = x0.expand(B, -1).contiguous()
@@ -174,9 +178,9 @@ class LQR:
             return states[0], actions[0], costs[0]
         return states, actions, costs
 
-    def solve(self, x0, T, terminal_zero=False):
-        """lqr.py:163-166 -> Trajectory (single problem) or BatchTrajectory"""
-        out, single = self._solve(x0, T, terminal_zero, want_policy=False, want_value=False)
+    def solve(self, x0, T, terminal_zero=False, batched=None):
+        """lqr.py:163-166 -> Trajectory (single problem) or BatchTrajectory (`batched=True` forces the batch reading of x0)"""
+        out, single = self._solve(x0, T, terminal_zero, want_policy=False, want_value=False, batched=batched)
         if single:
             if int(out["status"][0]) != 0:     # the reference raises here too (tf.linalg.inv of a singular Q_uu, lqr.py:84)
                 raise N.TfmpcError("LQR.solve: Q_uu is singular at some timestep (status %d)" % int(out["status"][0]))

@@ -93,3 +93,52 @@ def test_full_result_gather_world2(B):
     ret = mgr.dict()
     mp.spawn(_worker_full, args=(world, port, B, ret), nprocs=world, join=True)
     assert dict(ret) == {0: True, 1: True}
+
+
+class _StandInSolver:
+    """solve_device of the right shapes whose outputs are a per-problem function of the inputs, so that a shuffled and
+    re-assembled batch can be compared row by row with the unsharded call."""
+    def solve_device(self, x0, T, u_init):
+        b = x0.shape[0]
+        states = x0[:, None, :] + torch.arange(T + 1, dtype=x0.dtype)[None, :, None]
+        costs = (states ** 2).sum(-1) + torch.cat([u_init.abs().sum(-1), torch.zeros(b, 1, dtype=x0.dtype)], 1)
+        stats = torch.stack([(x0.abs().sum(1) * 7).to(torch.int32) % 100, torch.zeros(b, dtype=torch.int32),
+                             torch.zeros(b, dtype=torch.int32), (x0[:, 0] > 0).to(torch.int32)], 1)
+        return {"states": states, "actions": u_init.clone(), "costs": costs, "stats": stats}
+
+
+def _worker_permuted(rank, world, port, B, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from tfmpc_b200.sharding import shard_range, solve_sharded
+        T = 4
+        g = torch.Generator().manual_seed(1)
+        x0 = torch.randn(B, 2, generator=g)
+        u0 = torch.randn(B, T, 2, generator=g)
+        ref = _StandInSolver().solve_device(x0, T, u0)
+        local, full, perm = solve_sharded(_StandInSolver(), x0, T, u0, gather="full", permute_seed=5)
+        lo, hi = shard_range(B, rank, world)
+        ok = sorted(perm.tolist()) == list(range(B)) and all(torch.equal(full[k], ref[k]) for k in ref)
+        ok = ok and all(torch.equal(local[k], ref[k][perm[lo:hi]]) for k in ref)
+        _, (cost, its, st), perm2 = solve_sharded(_StandInSolver(), x0, T, u0, permute_seed=5)
+        ok = ok and torch.equal(perm, perm2) and torch.allclose(cost, ref["costs"].sum(1)) and torch.equal(its, ref["stats"][:, 0]) \
+            and torch.equal(st, ref["stats"][:, 3])
+        _, plain = solve_sharded(_StandInSolver(), x0, T, u0, gather="full")
+        ok = ok and all(torch.equal(plain[k], ref[k]) for k in ref)
+        ret[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("B", [9, 16])
+def test_solve_sharded_with_balancing_permutation_world2(B):
+    """solve_sharded(permute_seed=...): every rank draws the same shuffle, solves its block of the shuffled order, and the
+    gathered results (full or summaries) come back in the original problem order (a random permutation
+    before sharding evens out the ranks)."""
+    world, port = 2, _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker_permuted, args=(world, port, B, ret), nprocs=world, join=True)
+    assert dict(ret) == {0: True, 1: True}

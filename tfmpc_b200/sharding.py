@@ -72,16 +72,46 @@ def gather_results(out, batch, group=None):
     return full
 
 
-def solve_sharded(solver, x0, T, u_init, group=None, gather="summaries"):
+def balancing_permutation(batch, seed, device=None):
+    """The same pseudo-random order of `batch` problems on every rank (seeded host generator).  Iteration counts differ by up
+    to 10x between problems; when neighbouring problems are alike (a grid of initial states, sorted scenarios) contiguous
+    blocks give the ranks unequal work, and cutting the blocks from a shuffled order evens it out."""
+    perm = torch.randperm(int(batch), generator=torch.Generator().manual_seed(int(seed)))
+    return perm if device is None else perm.to(device)
+
+
+def unpermute(tensor, perm):
+    """Inverse of `tensor[perm]` along the leading axis."""
+    out = torch.empty_like(tensor)
+    out[perm] = tensor
+    return out
+
+
+def solve_sharded(solver, x0, T, u_init, group=None, gather="summaries", permute_seed=None):
     """iLQR solve of the global batch (x0 [B,n], u_init [B,T,m], identical on every rank): each rank solves its
     block on its own GPU, then the summaries are gathered.  Returns (local result dict, (cost, iterations, status)); with
-    gather="full" the second item is the dict of full-batch states / actions / costs / stats instead."""
+    gather="full" the second item is the dict of full-batch states / actions / costs / stats instead.
+
+    permute_seed: cut the blocks from a seeded shuffle of the problems instead of their given order (load balance across
+    ranks, see balancing_permutation); gathered results come back in the ORIGINAL order, the local dict holds this rank's
+    problems `perm[lo:hi]` in shuffled order, and the permutation is appended to the return value."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     B = x0.shape[0]
     lo, hi = shard_range(B, rank, world)
-    out = solver.solve_device(x0[lo:hi], T, u_init=u_init[lo:hi])
+    perm = None
+    if permute_seed is not None:
+        perm = balancing_permutation(B, permute_seed, x0.device)
+        mine = perm[lo:hi]
+        out = solver.solve_device(x0[mine].contiguous(), T, u_init=u_init[mine].contiguous())
+    else:
+        out = solver.solve_device(x0[lo:hi], T, u_init=u_init[lo:hi])
     if gather == "full":      # the gather SURVEY section 8(e) describes: costs, states, actions and iteration counts of every problem
-        return out, gather_results(out, B, group)
+        full = gather_results(out, B, group)
+        if perm is None:
+            return out, full
+        return out, {k: unpermute(v, perm) for k, v in full.items()}, perm
     summary = gather_summaries(out["costs"].sum(1), out["stats"][:, 0].contiguous(), out["stats"][:, 3].contiguous(), B, group)
-    return out, summary
+    if perm is None:
+        return out, summary
+    return out, tuple(unpermute(t, perm) for t in summary), perm
